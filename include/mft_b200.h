@@ -1,0 +1,109 @@
+/* mft_b200 -- C ABI of the B200-native MFT hot path (libmft_b200.so).
+ *
+ * This is the drop-in boundary: every entry point takes plain pointers and sizes (no torch
+ * types), launches hand-written sm_100a kernels on the caller's CUDA stream and returns 0 on
+ * success or a negative code (text via mftb200_last_error).  The reference is pure Python;
+ * each function cites the reference interface it stands in for (paths relative to the
+ * serycjon/MFT checkout).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Layouts (all device memory unless stated):
+ *   frame        uint8  (H, W, 3)   BGR, host or device          -- what MFT.track() receives
+ *   flow field   float  (4, H, W)   planar: flow_x, flow_y, occlusion in [0,1], sigma >= 0
+ *                                    == FlowOUTrackingResult.{flow, occlusion, sigma} stacked
+ *   chain index  uint8  (H, W)      position in the [inf, ascending delta] candidate order
+ */
+#ifndef MFT_B200_H
+#define MFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mftb200_ctx mftb200_ctx;
+typedef void* mftb200_stream;          /* cudaStream_t; NULL = default stream */
+
+#define MFTB200_OK 0
+#define MFTB200_ERR_ARG (-1)
+#define MFTB200_ERR_CUDA (-2)
+#define MFTB200_ERR_STATE (-3)
+#define MFTB200_ERR_DEVICE_FLAG (-4)   /* a kernel reported a pipeline time-out */
+
+#define MFTB200_NUM_LAYERS 47          /* packed conv layers, order documented in mft_b200/weights.py */
+#define MFTB200_MAX_PAIRS 8
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* Replaces RAFTWrapper.__init__ (MFT/raft.py:16-28): binds the calling thread's current CUDA
+ * device; fails unless it is compute capability 10.x. */
+int mftb200_create(mftb200_ctx** out);
+void mftb200_destroy(mftb200_ctx* ctx);
+const char* mftb200_last_error(const mftb200_ctx* ctx);   /* ctx may be NULL: creation errors */
+const char* mftb200_version(void);
+
+/* ---- weights (checkpoint consumed at MFT/raft.py:20-21) -------------------------------- */
+/* One packed layer: w_f16 = host fp16 [cout_pad][ktot] (K contiguous, K = taps x cin padded to
+ * 64), bias = host fp32 [bias_len], bias_len a multiple of 32 >= cout_pad. */
+int mftb200_upload_layer(mftb200_ctx* ctx, int layer, const uint16_t* w_f16, const float* bias, int cout_pad,
+                         int ktot, int bias_len);
+
+/* ---- geometry --------------------------------------------------------------------------- */
+/* Allocates workspace + builds TMA descriptors for H x W frames (any size >= 128; padded to a
+ * multiple of 8 like InputPadder, MFT/RAFT/core/utils/utils.py:7-24), up to max_pairs (<= 8)
+ * frame pairs per refine call, n_slots cached per-frame feature sets, `iters` GRU iterations
+ * (flow_config.flow_iters).  All layers must be uploaded first. */
+int mftb200_configure(mftb200_ctx* ctx, int H, int W, int max_pairs, int n_slots, int iters);
+
+/* ---- per-frame encoders (RAFT.forward part 1: MFT/RAFT/core/raft.py:122-149) ------------ */
+/* fnet + cnet of one frame, once, into feature slot `slot`.  bgr: (H,W,3) uint8; on_device=0
+ * means a host pointer (copied with cudaMemcpyAsync on `stream`; pin it for overlap). */
+int mftb200_encode_frame(mftb200_ctx* ctx, const uint8_t* bgr, int on_device, int slot, mftb200_stream stream);
+
+/* ---- batched RAFT refinement (RAFT.forward part 2 + RAFTWrapper.compute_flow post-processing:
+ * MFT/RAFT/core/raft.py:141-259, MFT/raft.py:56-62) ---------------------------------------- */
+/* For each pair p: flow left_slots[p] -> right_slots[p].  out: device float (n_pairs,4,H,W). */
+int mftb200_raft_refine(mftb200_ctx* ctx, int n_pairs, const int* left_slots, const int* right_slots, float* out,
+                        mftb200_stream stream);
+
+/* ---- chaining + selection (chain_results + selection block + invalid mask:
+ * MFT/MFT.py:114-142,233-239; MFT/results.py:87-136,250-265) ------------------------------ */
+/* left[k]: device (4,H,W) template->left_k result; right: device (K,4,H,W) left_k->current
+ * flows; out: device (4,H,W); index: device (H,W) uint8 or NULL.  Candidates must be ordered
+ * [inf, ascending delta] (MFT.py:114).  Context-free: usable without create/configure. */
+int mftb200_chain_select(int K, const float* const* left, const float* right, float occlusion_threshold, int H,
+                         int W, float* out, uint8_t* index, mftb200_stream stream);
+
+/* ---- FlowOUTrackingResult geometry (MFT/results.py:87-188) ------------------------------------ */
+/* warp_backward: out (C,H,W) = bilinear sample of img (C,H,W) at grid + flow (2,H,W), zeros outside,
+ * align_corners=True.  add_flow=1 with C == 2 gives FlowOUTrackingResult.chain (results.py:87-114). */
+int mftb200_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
+                          mftb200_stream stream);
+/* Point queries on a device field: out (C,N) = bilinear(field (C,H,W), points (N,2) xy).  add_points=1 adds
+ * the point itself to channels 0,1 == warp_forward_points (results.py:138-157); add_points=0 == sample()
+ * / interpolation.bilinear_sample (results.py:159-188, MFT/utils/interpolation.py:76-94). */
+int mftb200_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
+                          float* out, mftb200_stream stream);
+
+/* ---- diagnostics / test hooks ---------------------------------------------------------------- */
+int mftb200_device_error_flag(mftb200_ctx* ctx);          /* syncs; 0 = clean */
+/* key "conv_impl": 0 = tcgen05 (product), 1 = SIMT cross-check kernel (tests only). */
+int mftb200_set_option(mftb200_ctx* ctx, const char* key, int value);
+/* Named internal buffer for stage-level parity tests ("fmap_slots", "net_slots", "corr_l0", ...). */
+int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t* bytes);
+/* Copies the first `bytes` bytes of a named internal buffer into caller device memory (syncs). */
+int mftb200_debug_read(mftb200_ctx* ctx, const char* name, void* dst_device, size_t bytes);
+/* Number of kernels launched by this context since creation (bench's gpu_launches). */
+long long mftb200_launch_count(const mftb200_ctx* ctx);
+
+/* Stand-alone convolution through the product kernel, for unit tests: x fp16 NHWC
+ * (B,H,W,pitch) view of `cin` channels, packed weights as in upload_layer, taps = kh x kw
+ * centred window, stride 1|2, output fp32 NHWC (B,Ho,Wo,cout_pad) = (acc + bias) [relu]. */
+int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                        const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                        float* out_dev, int impl, mftb200_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFT_B200_H */

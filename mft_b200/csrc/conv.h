@@ -1,0 +1,89 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores: shared host/device definitions.
+//
+// One kernel serves every convolution of the RAFT-OU network and the all-pairs correlation:
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * Wt[cout, tap, cin]
+// A   : activations, NHWC fp16 in HBM, viewed through a 4-D TMA tensor map (C, W, H, B); the
+//       spatial shift of each tap is a coordinate offset of the TMA box, out-of-image taps are
+//       zero-filled by TMA (== the convolution's zero padding), stride 2 = TMA element stride.
+// Wt  : weights fp16 [cout][tap][cin padded to 64], K contiguous ("K-major"), 2-D tensor map.
+// D   : 128 pixels x n_tile couts, fp32, accumulated in TMEM; fused epilogue per EpiMode.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace mftb {
+
+enum EpiMode : int {
+    EPI_F16 = 0,     // bias (+relu) (+residual add, relu) -> fp16 NHWC slice
+    EPI_F32 = 1,     // (bias) * scale (+relu) -> fp32
+    EPI_CNET = 2,    // cols <128: tanh -> fp32 net ; cols >=128: relu -> fp16 inp   (core/raft.py:146-149)
+    EPI_GRU_ZR = 3,  // cols <128: z=sigmoid -> fp32 ; cols >=128: r=sigmoid, r*h -> fp16 (update.py:111-113)
+    EPI_GRU_Q = 4,   // q=tanh ; h=(1-z)h+zq -> fp32 master + fp16 copy               (update.py:114)
+    EPI_FLOW = 5,    // cols <2: delta_flow -> fp32 ; coords1 += delta                 (core/raft.py:184)
+    EPI_NUM_MODES = 6
+};
+
+constexpr int kMaxTaps = 9;
+constexpr int kTileM = 128;       // output pixels per CTA == TMEM lanes
+constexpr int kChunkK = 64;       // fp16 channels per pipeline stage (= one 128-byte swizzle row)
+
+struct ConvGeom {
+    int H, W;                     // OUTPUT height / width
+    int nbatch;                   // batch entries covered by this launch
+    int tile_h, tile_w;           // tile_h * tile_w == 128
+    int tiles_x, tiles_y;
+    int stride;                   // input step per output pixel (1 or 2)
+    int ntaps, kchunks;           // K loop = ntaps * kchunks stages of 64 channels
+    int8_t dy[kMaxTaps + 3], dx[kMaxTaps + 3];
+    int n_tile, n_tiles;          // couts per CTA (multiple of 16, <= 256), CTAs along cout
+    int b_rows_per_batch;         // B-matrix row offset per batch entry (correlation), 0 for weights
+    int stages, tmem_cols;
+};
+
+struct ConvEpi {
+    int relu;
+    float scale;
+    int n_valid;                  // couts that exist (columns >= n_valid are padding)
+    const float* bias;            // [n_tiles*n_tile] or nullptr
+    __half* out16; int out16_stride, out16_coff;
+    float* out32;  int out32_stride, out32_coff;
+    const __half* res16; int res_stride, res_coff;
+    float* h32;                   // GRU hidden state master [pixel][128]
+    float* z32;                   // GRU update gate scratch  [pixel][128]
+    float* coords1;               // [pixel][2]
+    float* delta32;               // [pixel][2]
+    int* err_flag;
+};
+
+// Fully described launch (built once per layer at configure time).
+struct ConvPlan {
+    CUtensorMap tmA, tmB;
+    ConvGeom g;
+    ConvEpi e;
+    int mode;
+    // raw views, used only by the SIMT cross-check kernel in tests
+    const __half* a_base; int a_pitch, a_cin, in_H, in_W;
+    const __half* b_base; int ktot;
+};
+
+struct TapList {
+    int n;
+    int8_t dy[kMaxTaps], dx[kMaxTaps];
+};
+TapList taps_rect(int kh, int kw);    // kh x kw window centred (odd sizes), row-major (ky, kx)
+
+// Picks (tile_h, tile_w) with tile_h*tile_w == 128 minimising padded work for an H x W map.
+void choose_tile(int H, int W, int* tile_h, int* tile_w);
+
+// Fills tensor maps + geometry.  a_base: first channel of the A view; a_pitch: fp16 elements per
+// pixel in HBM; a_cin: channels in the view (K beyond it reads as zero); in_H/in_W: INPUT dims.
+// wt: [cout_pad][ntaps*kchunks*64] fp16.  Returns nullptr on success or an error string.
+const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a_cin, int in_H, int in_W, int batch,
+                           int stride, const TapList& taps, const __half* wt, int cout_pad, int n_tile,
+                           int b_rows_per_batch, int force_tile_h, int force_tile_w);
+
+// Launch on `stream`; nbatch <= batch given at init.  use_simt=1 runs the SIMT cross-check kernel.
+const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt);
+
+}  // namespace mftb

@@ -1,0 +1,673 @@
+// Host-side engine behind the C ABI (include/mft_b200.h): weights, workspace, the launch
+// programs of the two encoders and of the batched refinement loop.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/mft_b200.h"
+#include "conv.h"
+#include "kernels.h"
+
+using namespace mftb;
+
+namespace {
+
+enum Layer : int {
+    // encoder layers: index within one encoder (fnet = +0, cnet = +16)
+    E_CONV1 = 0, E_L1_0_C1, E_L1_0_C2, E_L1_1_C1, E_L1_1_C2,
+    E_L2_0_C1, E_L2_0_C2, E_L2_0_DS, E_L2_1_C1, E_L2_1_C2,
+    E_L3_0_C1, E_L3_0_C2, E_L3_0_DS, E_L3_1_C1, E_L3_1_C2, E_CONV2,
+    L_FNET = 0, L_CNET = 16,
+    L_CONVC1 = 32, L_CONVC2, L_CONVF1, L_CONVF2, L_CONVM,
+    L_GRU_ZR1, L_GRU_Q1, L_GRU_ZR2, L_GRU_Q2,
+    L_FH1, L_FH2, L_MASK1, L_MASK2, L_OU1, L_OU2,
+    L_COUNT
+};
+static_assert(L_COUNT == MFTB200_NUM_LAYERS, "layer table out of sync with the header");
+
+struct LayerW {
+    __half* w = nullptr;
+    float* bias = nullptr;
+    int cout_pad = 0, ktot = 0;
+};
+
+struct Act {           // NHWC fp16 view
+    __half* base;
+    int pitch, C, H, W;
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct mftb200_ctx {
+    std::string err;
+    LayerW layers[L_COUNT];
+    bool configured = false;
+    int H = 0, W = 0, Hp = 0, Wp = 0, pad_l = 0, pad_t = 0, h = 0, w = 0, npx = 0;
+    int max_pairs = 0, n_slots = 0, iters = 12;
+    int conv_impl = 0;
+    long long launches = 0;
+    int* err_flag = nullptr;
+    std::vector<void*> allocs;
+
+    // encoder workspace
+    uint8_t* frame_u8 = nullptr;
+    __half* patches = nullptr;
+    __half* E[4] = {nullptr, nullptr, nullptr, nullptr};
+    __half* raw = nullptr;
+    __half* raw2 = nullptr;
+    double* sums = nullptr;
+    // slots
+    __half* fmap_slots = nullptr;
+    float* net_slots = nullptr;
+    __half* inp_slots = nullptr;
+    // refinement workspace
+    int* slot_table = nullptr;
+    __half *F1 = nullptr, *F2 = nullptr, *corr16 = nullptr, *flowpatch = nullptr, *c1buf = nullptr, *cf = nullptr,
+           *f1buf = nullptr, *X = nullptr, *fhbuf = nullptr, *oupack = nullptr;
+    float *corr[4] = {nullptr, nullptr, nullptr, nullptr}, *h32 = nullptr, *z32 = nullptr, *coords1 = nullptr,
+          *delta32 = nullptr, *mask32 = nullptr, *ou32 = nullptr, *out = nullptr;
+    size_t corr_bytes[4] = {0, 0, 0, 0};
+
+    std::vector<ConvPlan> plans;
+    using Step = std::function<const char*(mftb200_ctx*, cudaStream_t)>;
+    std::vector<Step> enc_steps, pre_steps, iter_steps, final_steps;
+    int cur_slot = 0, cur_pairs = 0;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    template <class T>
+    T* dalloc(size_t n) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(T) + 256) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, n * sizeof(T) + 256);
+        allocs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    void free_workspace() {
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+        plans.clear();
+        enc_steps.clear(); pre_steps.clear(); iter_steps.clear(); final_steps.clear();
+        configured = false;
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// program construction helpers
+// ------------------------------------------------------------------------------------------
+struct Builder {
+    mftb200_ctx* c;
+    const char* err = nullptr;
+
+    // Adds a conv plan; returns its index (or -1 and sets err).
+    int conv(int layer, Act in, int batch, int stride, TapList taps, int n_tile, int mode, int force_th = 0,
+             int force_tw = 0, const __half* bmat = nullptr, int b_rows = 0, int cout = 0) {
+        if (err) return -1;
+        ConvPlan p;
+        const LayerW* L = layer >= 0 ? &c->layers[layer] : nullptr;
+        const __half* wt = L ? L->w : bmat;
+        const int cout_pad = L ? L->cout_pad : cout;
+        const char* e = conv_plan_init(&p, in.base, in.pitch, in.C, in.H, in.W, batch, stride, taps, wt, cout_pad,
+                                       n_tile, b_rows, force_th, force_tw);
+        if (e) { err = e; return -1; }
+        if (L && p.ktot != L->ktot) {
+            static char buf[128];
+            snprintf(buf, sizeof buf, "layer %d: packed K %d does not match plan K %d", layer, L->ktot, p.ktot);
+            err = buf;
+            return -1;
+        }
+        p.mode = mode;
+        p.e.bias = L ? L->bias : nullptr;
+        p.e.scale = 1.0f;
+        p.e.n_valid = cout_pad;
+        p.e.err_flag = c->err_flag;
+        c->plans.push_back(p);
+        return static_cast<int>(c->plans.size()) - 1;
+    }
+    ConvEpi& epi(int i) { return c->plans[i].e; }
+    // conv with fp16 output
+    int conv16(int layer, Act in, int batch, int stride, TapList taps, int n_tile, int relu, __half* out, int out_stride,
+               int out_coff, int n_valid, const __half* res = nullptr, int res_stride = 0) {
+        const int i = conv(layer, in, batch, stride, taps, n_tile, EPI_F16);
+        if (i < 0) return i;
+        ConvEpi& e = epi(i);
+        e.relu = relu; e.out16 = out; e.out16_stride = out_stride; e.out16_coff = out_coff; e.n_valid = n_valid;
+        e.res16 = res; e.res_stride = res_stride; e.res_coff = 0;
+        return i;
+    }
+};
+
+mftb200_ctx::Step conv_step(int plan_idx, bool batched_pairs) {
+    return [plan_idx, batched_pairs](mftb200_ctx* c, cudaStream_t s) -> const char* {
+        c->launches++;
+        return conv_launch(c->plans[plan_idx], batched_pairs ? c->cur_pairs : 1, s, c->conv_impl);
+    };
+}
+
+const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
+    const bool inorm = (net == L_FNET);
+    const int H2 = c->Hp / 2, W2 = c->Wp / 2, H4 = c->Hp / 4, W4 = c->Wp / 4, H8 = c->h, W8 = c->w;
+    const int P2 = H2 * W2;
+    auto& S = c->enc_steps;
+    const TapList t1 = taps_rect(1, 1), t3 = taps_rect(3, 3);
+
+    // raw -> instance norm (+relu) (+residual) -> out
+    auto norm = [&](__half* raw, int P, int C, int relu, const __half* res, __half* out) {
+        S.push_back([=](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+            launch_instnorm_stats(raw, 1, P, C, cc->sums, s);
+            launch_instnorm_apply(raw, cc->sums, 1, P, C, relu, res, out, s);
+            cc->launches += 2;
+            return nullptr;
+        });
+    };
+
+    // conv1 (7x7/2 via im2col patches): 1x1 GEMM over [P2][147]
+    {
+        Act in{c->patches, 152, 147, 1, P2};
+        if (inorm) {
+            S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 0, c->raw, 64, 0, 64), false));
+            norm(c->raw, P2, 64, 1, nullptr, c->E[0]);
+        } else {
+            S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 1, c->E[0], 64, 0, 64), false));
+        }
+    }
+    struct Blk { int c1, c2, ds, cin, cout, stride, Hin, Win; };
+    const Blk blks[6] = {
+        {E_L1_0_C1, E_L1_0_C2, -1, 64, 64, 1, H2, W2},   {E_L1_1_C1, E_L1_1_C2, -1, 64, 64, 1, H2, W2},
+        {E_L2_0_C1, E_L2_0_C2, E_L2_0_DS, 64, 96, 2, H2, W2}, {E_L2_1_C1, E_L2_1_C2, -1, 96, 96, 1, H4, W4},
+        {E_L3_0_C1, E_L3_0_C2, E_L3_0_DS, 96, 128, 2, H4, W4}, {E_L3_1_C1, E_L3_1_C2, -1, 128, 128, 1, H8, W8}};
+    int cur = 0;   // index of the buffer holding the block input
+    for (const Blk& b : blks) {
+        __half* in = c->E[cur];
+        __half* out = c->E[cur ^ 1];
+        __half* tmp = c->E[2];
+        __half* xd = c->E[3];
+        const int Ho = b.Hin / b.stride, Wo = b.Win / b.stride, Po = Ho * Wo;
+        Act ain{in, b.cin, b.cin, b.Hin, b.Win};
+        Act atmp{tmp, b.cout, b.cout, Ho, Wo};
+        const __half* res = in;
+        if (inorm) {
+            S.push_back(conv_step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
+            norm(c->raw, Po, b.cout, 1, nullptr, tmp);
+            if (b.ds >= 0) {
+                S.push_back(conv_step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, c->raw2, b.cout, 0, b.cout), false));
+                norm(c->raw2, Po, b.cout, 0, nullptr, xd);
+                res = xd;
+            }
+            S.push_back(conv_step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
+            norm(c->raw, Po, b.cout, 1, res, out);
+        } else {
+            S.push_back(conv_step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 1, tmp, b.cout, 0, b.cout), false));
+            if (b.ds >= 0) {
+                S.push_back(conv_step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, xd, b.cout, 0, b.cout), false));
+                res = xd;
+            }
+            S.push_back(conv_step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 1, out, b.cout, 0, b.cout, res, b.cout), false));
+        }
+        cur ^= 1;
+    }
+    // conv2 (1x1 128 -> 256) into the feature slot
+    {
+        Act in{c->E[cur], 128, 128, H8, W8};
+        const int mode = inorm ? EPI_F16 : EPI_CNET;
+        const int i = B.conv(net + E_CONV2, in, 1, 1, t1, 256, mode);
+        if (i >= 0) {
+            ConvEpi& e = B.epi(i);
+            e.n_valid = 256; e.out16_stride = 256;
+        }
+        S.push_back([i, inorm](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+            ConvPlan p = cc->plans[i];
+            const size_t off = static_cast<size_t>(cc->cur_slot) * cc->npx;
+            if (inorm) {
+                p.e.out16 = cc->fmap_slots + off * 256;
+            } else {
+                p.e.out32 = cc->net_slots + off * 128;
+                p.e.out16 = cc->inp_slots + off * 128;
+            }
+            cc->launches++;
+            return conv_launch(p, 1, s, cc->conv_impl);
+        });
+    }
+    return B.err;
+}
+
+const char* build_refine(mftb200_ctx* c, Builder& B) {
+    const int h = c->h, w = c->w, npx = c->npx, mp = c->max_pairs;
+    const TapList t1 = taps_rect(1, 1), t3 = taps_rect(3, 3), t15 = taps_rect(1, 5), t51 = taps_rect(5, 1);
+
+    // ---- once per call: gather features, build correlation pyramid -------------------------
+    c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        PairSetup a{cc->slot_table, cc->fmap_slots, cc->net_slots, cc->inp_slots, cc->F1, cc->F2, cc->h32, cc->X,
+                    cc->coords1, cc->cur_pairs, cc->h, cc->w};
+        launch_pair_setup(a, s);
+        cc->launches++;
+        return nullptr;
+    });
+    {   // all-pairs correlation: D[n1, n2] = <F1[n1,:], F2[n2,:]> / sqrt(256)   (core/corr.py:53-69)
+        Act in{c->F1, 256, 256, 1, npx};
+        const int i = B.conv(-1, in, mp, 1, t1, 256, EPI_F32, 1, 128, c->F2, npx, npx);
+        if (i >= 0) {
+            ConvEpi& e = B.epi(i);
+            e.scale = 0.0625f; e.out32 = c->corr[0]; e.out32_stride = npx; e.out32_coff = 0; e.n_valid = npx;
+        }
+        c->pre_steps.push_back(conv_step(i, true));
+    }
+    c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        launch_corr_pool(cc->corr[0], cc->corr[1], cc->corr[2], cc->corr[3], static_cast<long>(cc->cur_pairs) * cc->npx,
+                         cc->h, cc->w, s);
+        cc->launches++;
+        return nullptr;
+    });
+
+    // ---- one GRU iteration (core/raft.py:173-184, core/update.py:229-238) ------------------
+    auto& S = c->iter_steps;
+    S.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        LookupArgs a{{cc->corr[0], cc->corr[1], cc->corr[2], cc->corr[3]}, cc->coords1, cc->corr16, cc->flowpatch,
+                     cc->X, cc->cur_pairs, cc->h, cc->w};
+        launch_lookup(a, s);
+        cc->launches++;
+        return nullptr;
+    });
+    Act a_corr{c->corr16, 328, 324, h, w};
+    Act a_c1{c->c1buf, 256, 256, h, w};
+    Act a_fp{c->flowpatch, 104, 98, h, w};
+    Act a_f1{c->f1buf, 128, 128, h, w};
+    Act a_cf{c->cf, 256, 256, h, w};
+    Act a_hx{c->X, 512, 384, h, w};            // h | inp | motion
+    Act a_qx{c->X + 128, 512, 384, h, w};      // inp | motion | r*h
+    Act a_h{c->X, 512, 128, h, w};
+    Act a_fh{c->fhbuf, 256, 256, h, w};
+    // motion encoder (update.py:152-160)
+    S.push_back(conv_step(B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
+    S.push_back(conv_step(B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
+    S.push_back(conv_step(B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
+    S.push_back(conv_step(B.conv16(L_CONVF2, a_f1, mp, 1, t3, 64, 1, c->cf, 256, 192, 64), true));
+    S.push_back(conv_step(B.conv16(L_CONVM, a_cf, mp, 1, t3, 128, 1, c->X, 512, 256, 126), true));
+    // SepConvGRU (update.py:108-123): horizontal 1x5 then vertical 5x1
+    for (int pass = 0; pass < 2; ++pass) {
+        const TapList& tp = pass == 0 ? t15 : t51;
+        const int izr = B.conv(pass == 0 ? L_GRU_ZR1 : L_GRU_ZR2, a_hx, mp, 1, tp, 256, EPI_GRU_ZR);
+        if (izr >= 0) {
+            ConvEpi& e = B.epi(izr);
+            e.n_valid = 256; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 384;
+        }
+        S.push_back(conv_step(izr, true));
+        const int iq = B.conv(pass == 0 ? L_GRU_Q1 : L_GRU_Q2, a_qx, mp, 1, tp, 128, EPI_GRU_Q);
+        if (iq >= 0) {
+            ConvEpi& e = B.epi(iq);
+            e.n_valid = 128; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 0;
+        }
+        S.push_back(conv_step(iq, true));
+    }
+    // flow head (update.py:6-14) ; coords1 += delta_flow (core/raft.py:184)
+    S.push_back(conv_step(B.conv16(L_FH1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    {
+        const int i = B.conv(L_FH2, a_fh, mp, 1, t3, 16, EPI_FLOW);
+        if (i >= 0) {
+            ConvEpi& e = B.epi(i);
+            e.n_valid = 2; e.coords1 = c->coords1; e.delta32 = c->delta32;
+        }
+        S.push_back(conv_step(i, true));
+    }
+
+    // ---- after the last iteration: mask head, OU head, convex upsampling ---------------------
+    auto& Fz = c->final_steps;
+    Fz.push_back(conv_step(B.conv16(L_MASK1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    {
+        const int i = B.conv(L_MASK2, a_fh, mp, 1, t1, 192, EPI_F32);
+        if (i >= 0) {
+            ConvEpi& e = B.epi(i);
+            e.scale = 0.25f; e.out32 = c->mask32; e.out32_stride = 576; e.n_valid = 576;   // update.py:237
+        }
+        Fz.push_back(conv_step(i, true));
+    }
+    Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        OuPackArgs a{cc->X, cc->corr16, cc->coords1, cc->delta32, cc->oupack, cc->cur_pairs, cc->h, cc->w};
+        launch_ou_pack(a, s);
+        cc->launches++;
+        return nullptr;
+    });
+    Act a_ou{c->oupack, 720, 712, h, w};
+    Fz.push_back(conv_step(B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    {
+        const int i = B.conv(L_OU2, a_fh, mp, 1, t3, 16, EPI_F32);
+        if (i >= 0) {
+            ConvEpi& e = B.epi(i);
+            e.out32 = c->ou32; e.out32_stride = 4; e.n_valid = 3;
+        }
+        Fz.push_back(conv_step(i, true));
+    }
+    Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        UpsampleArgs a{cc->mask32, cc->coords1, cc->ou32, cc->out, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
+                       cc->pad_l, cc->pad_t};
+        launch_upsample(a, s);
+        cc->launches++;
+        return nullptr;
+    });
+    return B.err;
+}
+
+int run_steps(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cudaStream_t s) {
+    for (auto& st : steps) {
+        if (const char* e = st(c, s)) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+    }
+    return MFTB200_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* mftb200_version(void) { return "mft_b200 0.1 (sm_100a)"; }
+
+const char* mftb200_last_error(const mftb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mftb200_create(mftb200_ctx** out) {
+    if (!out) return MFTB200_ERR_ARG;
+    *out = nullptr;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        g_create_error = "no CUDA device";
+        return MFTB200_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "mft_b200 needs a compute-capability 10.x GPU (B200); found " + std::string(prop.name);
+        return MFTB200_ERR_CUDA;
+    }
+    mftb200_ctx* c = new mftb200_ctx();
+    if (cudaMalloc(reinterpret_cast<void**>(&c->err_flag), 256) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed";
+        delete c;
+        return MFTB200_ERR_CUDA;
+    }
+    cudaMemset(c->err_flag, 0, 256);
+    *out = c;
+    return MFTB200_OK;
+}
+
+void mftb200_destroy(mftb200_ctx* c) {
+    if (!c) return;
+    c->free_workspace();
+    for (auto& L : c->layers) {
+        cudaFree(L.w);
+        cudaFree(L.bias);
+    }
+    cudaFree(c->err_flag);
+    delete c;
+}
+
+int mftb200_upload_layer(mftb200_ctx* c, int layer, const uint16_t* w_f16, const float* bias, int cout_pad, int ktot,
+                         int bias_len) {
+    if (!c) return MFTB200_ERR_ARG;
+    if (layer < 0 || layer >= L_COUNT || !w_f16 || !bias || cout_pad <= 0 || ktot <= 0 || ktot % 64 != 0 ||
+        bias_len < cout_pad || bias_len % 32 != 0)
+        return c->fail(MFTB200_ERR_ARG, "upload_layer(%d): bad arguments", layer);
+    LayerW& L = c->layers[layer];
+    cudaFree(L.w);
+    cudaFree(L.bias);
+    L = LayerW();
+    const size_t wb = static_cast<size_t>(cout_pad) * ktot * 2;
+    if (cudaMalloc(reinterpret_cast<void**>(&L.w), wb) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&L.bias), (bias_len + 32) * sizeof(float)) != cudaSuccess)
+        return c->fail(MFTB200_ERR_CUDA, "upload_layer(%d): cudaMalloc failed", layer);
+    cudaMemset(L.bias, 0, (bias_len + 32) * sizeof(float));
+    if (cudaMemcpy(L.w, w_f16, wb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(L.bias, bias, bias_len * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        return c->fail(MFTB200_ERR_CUDA, "upload_layer(%d): copy failed", layer);
+    L.cout_pad = cout_pad;
+    L.ktot = ktot;
+    return MFTB200_OK;
+}
+
+int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, int iters) {
+    if (!c) return MFTB200_ERR_ARG;
+    if (H < 128 || W < 128 || max_pairs < 1 || max_pairs > MFTB200_MAX_PAIRS || n_slots < 2 || iters < 1)
+        return c->fail(MFTB200_ERR_ARG, "configure: bad arguments (H,W >= 128, 1 <= max_pairs <= 8, n_slots >= 2)");
+    for (int i = 0; i < L_COUNT; ++i)
+        if (!c->layers[i].w) return c->fail(MFTB200_ERR_STATE, "configure: layer %d not uploaded", i);
+    c->free_workspace();
+    c->H = H; c->W = W;
+    const int ph = (8 - H % 8) % 8, pw = (8 - W % 8) % 8;
+    c->pad_t = ph / 2; c->pad_l = pw / 2;
+    c->Hp = H + ph; c->Wp = W + pw;
+    c->h = c->Hp / 8; c->w = c->Wp / 8; c->npx = c->h * c->w;
+    c->max_pairs = max_pairs; c->n_slots = n_slots; c->iters = iters;
+    const size_t P2 = static_cast<size_t>(c->Hp / 2) * (c->Wp / 2);
+    const size_t npx = c->npx, M = npx * max_pairs;
+    bool ok = true;
+    auto chk = [&](void* p) { ok = ok && p != nullptr; };
+    chk(c->frame_u8 = c->dalloc<uint8_t>(static_cast<size_t>(H) * W * 3));
+    chk(c->patches = c->dalloc<__half>(P2 * 152));
+    for (int i = 0; i < 4; ++i) chk(c->E[i] = c->dalloc<__half>(P2 * 64));
+    chk(c->raw = c->dalloc<__half>(P2 * 64));
+    chk(c->raw2 = c->dalloc<__half>(P2 * 64));
+    chk(c->sums = c->dalloc<double>(2 * 256));
+    chk(c->fmap_slots = c->dalloc<__half>(npx * 256 * n_slots));
+    chk(c->net_slots = c->dalloc<float>(npx * 128 * n_slots));
+    chk(c->inp_slots = c->dalloc<__half>(npx * 128 * n_slots));
+    chk(c->slot_table = c->dalloc<int>(2 * MFTB200_MAX_PAIRS));
+    chk(c->F1 = c->dalloc<__half>(M * 256));
+    chk(c->F2 = c->dalloc<__half>(M * 256));
+    int hl = c->h, wl = c->w;
+    for (int l = 0; l < 4; ++l) {
+        c->corr_bytes[l] = M * hl * wl * sizeof(float);
+        chk(c->corr[l] = c->dalloc<float>(M * hl * wl));
+        hl /= 2; wl /= 2;
+    }
+    chk(c->corr16 = c->dalloc<__half>(M * 328));
+    chk(c->flowpatch = c->dalloc<__half>(M * 104));
+    chk(c->c1buf = c->dalloc<__half>(M * 256));
+    chk(c->cf = c->dalloc<__half>(M * 256));
+    chk(c->f1buf = c->dalloc<__half>(M * 128));
+    chk(c->X = c->dalloc<__half>(M * 512));
+    chk(c->fhbuf = c->dalloc<__half>(M * 256));
+    chk(c->oupack = c->dalloc<__half>(M * 720));
+    chk(c->h32 = c->dalloc<float>(M * 128));
+    chk(c->z32 = c->dalloc<float>(M * 128));
+    chk(c->coords1 = c->dalloc<float>(M * 2));
+    chk(c->delta32 = c->dalloc<float>(M * 2));
+    chk(c->mask32 = c->dalloc<float>(M * 576));
+    chk(c->ou32 = c->dalloc<float>(M * 4));
+    chk(c->out = c->dalloc<float>(static_cast<size_t>(max_pairs) * 4 * H * W));
+    if (!ok) {
+        c->free_workspace();
+        return c->fail(MFTB200_ERR_CUDA, "configure: out of device memory");
+    }
+    Builder B{c};
+    c->plans.reserve(128);
+    c->enc_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        launch_frame_patches(cc->frame_u8, cc->H, cc->W, cc->Hp, cc->Wp, cc->pad_l, cc->pad_t, cc->patches, s);
+        cc->launches++;
+        return nullptr;
+    });
+    const char* e = build_encoder(c, B, L_FNET);
+    if (!e) e = build_encoder(c, B, L_CNET);
+    if (!e) e = build_refine(c, B);
+    if (e) {
+        std::string msg = e;
+        c->free_workspace();
+        return c->fail(MFTB200_ERR_CUDA, "configure: %s", msg.c_str());
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return c->fail(MFTB200_ERR_CUDA, "configure: device error");
+    c->configured = true;
+    return MFTB200_OK;
+}
+
+int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int slot, mftb200_stream stream) {
+    if (!c) return MFTB200_ERR_ARG;
+    if (!c->configured) return c->fail(MFTB200_ERR_STATE, "encode_frame: not configured");
+    if (!bgr || slot < 0 || slot >= c->n_slots) return c->fail(MFTB200_ERR_ARG, "encode_frame: bad slot %d", slot);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t bytes = static_cast<size_t>(c->H) * c->W * 3;
+    if (cudaMemcpyAsync(c->frame_u8, bgr, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s) !=
+        cudaSuccess)
+        return c->fail(MFTB200_ERR_CUDA, "encode_frame: frame copy failed");
+    c->cur_slot = slot;
+    return run_steps(c, c->enc_steps, s);
+}
+
+int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, const int* right_slots, float* out,
+                        mftb200_stream stream) {
+    if (!c) return MFTB200_ERR_ARG;
+    if (!c->configured) return c->fail(MFTB200_ERR_STATE, "raft_refine: not configured");
+    if (n_pairs < 1 || n_pairs > c->max_pairs || !left_slots || !right_slots || !out)
+        return c->fail(MFTB200_ERR_ARG, "raft_refine: bad arguments");
+    int table[2 * MFTB200_MAX_PAIRS];
+    for (int p = 0; p < n_pairs; ++p) {
+        if (left_slots[p] < 0 || left_slots[p] >= c->n_slots || right_slots[p] < 0 || right_slots[p] >= c->n_slots)
+            return c->fail(MFTB200_ERR_ARG, "raft_refine: slot out of range");
+        table[2 * p] = left_slots[p];
+        table[2 * p + 1] = right_slots[p];
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // pageable source: the runtime stages the copy before returning, so `table` may go out of scope
+    if (cudaMemcpyAsync(c->slot_table, table, sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return c->fail(MFTB200_ERR_CUDA, "raft_refine: slot table copy failed");
+    c->cur_pairs = n_pairs;
+    int r = run_steps(c, c->pre_steps, s);
+    for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) r = run_steps(c, c->iter_steps, s);
+    if (r == MFTB200_OK) r = run_steps(c, c->final_steps, s);
+    if (r != MFTB200_OK) return r;
+    if (cudaMemcpyAsync(out, c->out, sizeof(float) * 4 * n_pairs * c->H * c->W, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        return c->fail(MFTB200_ERR_CUDA, "raft_refine: output copy failed");
+    return MFTB200_OK;
+}
+
+int mftb200_chain_select(int K, const float* const* left, const float* right, float occlusion_threshold, int H, int W,
+                         float* out, uint8_t* index, mftb200_stream stream) {
+    if (K < 1 || K > kMaxChains || !left || !right || !out || H < 2 || W < 2) return MFTB200_ERR_ARG;
+    ChainSelectArgs a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < K; ++k) {
+        if (!left[k]) return MFTB200_ERR_ARG;
+        a.left[k] = left[k];
+    }
+    a.right = right; a.out = out; a.index = index; a.K = K; a.H = H; a.W = W;
+    a.occlusion_threshold = occlusion_threshold;
+    launch_chain_select(a, static_cast<cudaStream_t>(stream));
+    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+}
+
+int mftb200_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
+                          mftb200_stream stream) {
+    if (!flow || !img || !out || C < 1 || H < 2 || W < 2 || (add_flow && C != 2)) return MFTB200_ERR_ARG;
+    launch_warp_backward(flow, img, C, H, W, add_flow, out, static_cast<cudaStream_t>(stream));
+    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+}
+
+int mftb200_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
+                          float* out, mftb200_stream stream) {
+    if (!field || !points_xy || !out || C < 1 || H < 2 || W < 2 || N < 0) return MFTB200_ERR_ARG;
+    launch_sample_points(field, C, H, W, points_xy, N, add_points, out, static_cast<cudaStream_t>(stream));
+    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+}
+
+int mftb200_device_error_flag(mftb200_ctx* c) {
+    if (!c) return MFTB200_ERR_ARG;
+    int v = 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return c->fail(MFTB200_ERR_CUDA, "device error: %s", cudaGetErrorString(e));
+    cudaMemcpy(&v, c->err_flag, sizeof v, cudaMemcpyDeviceToHost);
+    if (v != 0) {
+        cudaMemset(c->err_flag, 0, sizeof v);
+        return c->fail(MFTB200_ERR_DEVICE_FLAG, "a kernel reported a pipeline time-out (warp role %d)", v - 1);
+    }
+    return 0;
+}
+
+int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
+    if (!c || !key) return MFTB200_ERR_ARG;
+    if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
+    return c->fail(MFTB200_ERR_ARG, "set_option: unknown key %s", key);
+}
+
+long long mftb200_launch_count(const mftb200_ctx* c) { return c ? c->launches : 0; }
+
+int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* bytes) {
+    if (!c || !name || !ptr || !bytes) return MFTB200_ERR_ARG;
+    if (!c->configured) return c->fail(MFTB200_ERR_STATE, "debug_buffer: not configured");
+    const size_t npx = c->npx, M = npx * c->max_pairs;
+    struct Ent { const char* n; void* p; size_t b; };
+    const Ent tab[] = {
+        {"fmap_slots", c->fmap_slots, npx * 256 * c->n_slots * 2}, {"net_slots", c->net_slots, npx * 128 * c->n_slots * 4},
+        {"inp_slots", c->inp_slots, npx * 128 * c->n_slots * 2},  {"corr_l0", c->corr[0], c->corr_bytes[0]},
+        {"corr_l1", c->corr[1], c->corr_bytes[1]}, {"corr_l2", c->corr[2], c->corr_bytes[2]},
+        {"corr_l3", c->corr[3], c->corr_bytes[3]}, {"corr16", c->corr16, M * 328 * 2}, {"X", c->X, M * 512 * 2},
+        {"h32", c->h32, M * 128 * 4}, {"coords1", c->coords1, M * 2 * 4}, {"delta32", c->delta32, M * 2 * 4},
+        {"mask32", c->mask32, M * 576 * 4}, {"ou32", c->ou32, M * 4 * 4}, {"patches", c->patches, 0},
+        {"E0", c->E[0], 0}, {"E1", c->E[1], 0}, {"flowpatch", c->flowpatch, M * 104 * 2}, {"cf", c->cf, M * 256 * 2},
+    };
+    for (const Ent& e : tab)
+        if (strcmp(e.n, name) == 0) { *ptr = e.p; *bytes = e.b; return MFTB200_OK; }
+    return c->fail(MFTB200_ERR_ARG, "debug_buffer: unknown buffer %s", name);
+}
+
+int mftb200_debug_read(mftb200_ctx* c, const char* name, void* dst_device, size_t bytes) {
+    void* src = nullptr;
+    size_t avail = 0;
+    const int r = mftb200_debug_buffer(c, name, &src, &avail);
+    if (r != MFTB200_OK) return r;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(dst_device, src, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess)
+        return c->fail(MFTB200_ERR_CUDA, "debug_read(%s): copy failed", name);
+    return MFTB200_OK;
+}
+
+int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                        const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                        float* out_dev, int impl, mftb200_stream stream) {
+    if (!x_dev || !w_dev || !out_dev || kh * kw > kMaxTaps) return MFTB200_ERR_ARG;
+    ConvPlan p;
+    const char* e = conv_plan_init(&p, reinterpret_cast<const __half*>(x_dev), pitch, cin, H, W, B, stride,
+                                   taps_rect(kh, kw), reinterpret_cast<const __half*>(w_dev), cout_pad, n_tile, 0, 0, 0);
+    if (e) {
+        g_create_error = e;
+        return MFTB200_ERR_CUDA;
+    }
+    static int* flag = nullptr;
+    if (!flag) {
+        cudaMalloc(reinterpret_cast<void**>(&flag), 256);
+        cudaMemset(flag, 0, 256);
+    }
+    p.mode = EPI_F32;
+    p.e.bias = bias_dev; p.e.scale = 1.0f; p.e.relu = relu; p.e.n_valid = cout_pad;
+    p.e.out32 = out_dev; p.e.out32_stride = cout_pad; p.e.out32_coff = 0; p.e.err_flag = flag;
+    e = conv_launch(p, B, static_cast<cudaStream_t>(stream), impl);
+    if (e) {
+        g_create_error = e;
+        return MFTB200_ERR_CUDA;
+    }
+    cudaError_t ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (ce != cudaSuccess) {
+        g_create_error = cudaGetErrorString(ce);
+        return MFTB200_ERR_CUDA;
+    }
+    int v = 0;
+    cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost);
+    if (v) {
+        cudaMemset(flag, 0, sizeof v);
+        g_create_error = "conv kernel pipeline time-out (warp role " + std::to_string(v - 1) + ")";
+        return MFTB200_ERR_DEVICE_FLAG;
+    }
+    return MFTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// Bandwidth-bound kernels of the MFT hot path.  Compiled with --fmad=false: the chaining /
+// selection / lookup arithmetic follows a defined fp32 operation order (one rounding per
+// operation, no contraction) so that results are bit-identical to oracle/mft_oracle.py.
+#include "kernels.h"
+
+#include <cmath>
+
+namespace mftb {
+
+// ==========================================================================================
+// shared bilinear helper: the reference feeds pixel coordinates through a normalise ->
+// grid_sample(align_corners=True) round trip (MFT/utils/interpolation.py:63-73 and
+// MFT/RAFT/core/utils/utils.py:98-106); ATen undoes it as ((g+1)/2)*(size-1).
+// ==========================================================================================
+__device__ __forceinline__ float roundtrip_mul(float c, float scale, float size_m1) {
+    const float g = c * scale - 1.0f;                    // normalize_coords: x*(2/(W-1)) - 1
+    return ((g + 1.0f) / 2.0f) * size_m1;
+}
+__device__ __forceinline__ float roundtrip_div(float c, float size_m1) {
+    const float g = (2.0f * c) / size_m1 - 1.0f;         // bilinear_sampler: 2*x/(W-1) - 1
+    return ((g + 1.0f) / 2.0f) * size_m1;
+}
+
+// ==========================================================================================
+// chain + select  (MFT/MFT.py:114-142,233-239 ; MFT/results.py:87-136,250-265)
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+chain_select_kernel(const ChainSelectArgs a, const float sx, const float sy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= a.W) return;
+    const long hw = static_cast<long>(a.H) * a.W;
+    const long p = static_cast<long>(y) * a.W + x;
+    const float gx = static_cast<float>(x), gy = static_cast<float>(y);
+    const float wm1 = static_cast<float>(a.W - 1), hm1 = static_cast<float>(a.H - 1);
+    const float ninf = -INFINITY;
+
+    float bfx = 0.f, bfy = 0.f, bocc = 0.f, bsig = 0.f, bscore = 0.f;
+    int bidx = 0;
+    for (int k = 0; k < a.K; ++k) {
+        const float* L = a.left[k];
+        const float lfx = __ldg(L + p), lfy = __ldg(L + hw + p), locc = __ldg(L + 2 * hw + p), lsig = __ldg(L + 3 * hw + p);
+        const float px = gx + lfx, py = gy + lfy;
+        const float ix = roundtrip_mul(px, sx, wm1), iy = roundtrip_mul(py, sy, hm1);
+        float s0, s1, s2, s3;
+        if (!(isfinite(ix) && isfinite(iy))) {
+            s0 = s1 = s2 = s3 = NAN;
+        } else {
+            const float x0f = floorf(ix), y0f = floorf(iy);
+            const float wE = ix - x0f, wW = 1.0f - wE, wS = iy - y0f, wN = 1.0f - wS;
+            const int x0 = static_cast<int>(fminf(fmaxf(x0f, -2.0f), static_cast<float>(a.W + 1)));
+            const int y0 = static_cast<int>(fminf(fmaxf(y0f, -2.0f), static_cast<float>(a.H + 1)));
+            const bool xw = x0 >= 0 && x0 < a.W, xe = x0 + 1 >= 0 && x0 + 1 < a.W;
+            const bool yn = y0 >= 0 && y0 < a.H, ys = y0 + 1 >= 0 && y0 + 1 < a.H;
+            const float* R = a.right + static_cast<long>(k) * 4 * hw;
+            const long onw = static_cast<long>(y0) * a.W + x0;
+            const float cnw = wW * wN, cne = wE * wN, csw = wW * wS, cse = wE * wS;
+            float s[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float* Rc = R + c * hw;
+                const float vnw = (xw && yn) ? __ldg(Rc + onw) : 0.0f;
+                const float vne = (xe && yn) ? __ldg(Rc + onw + 1) : 0.0f;
+                const float vsw = (xw && ys) ? __ldg(Rc + onw + a.W) : 0.0f;
+                const float vse = (xe && ys) ? __ldg(Rc + onw + a.W + 1) : 0.0f;
+                float o = cnw * vnw;
+                o = o + cne * vne;
+                o = o + csw * vsw;
+                o = o + cse * vse;
+                s[c] = o;
+            }
+            s0 = s[0]; s1 = s[1]; s2 = s[2]; s3 = s[3];
+        }
+        const float fx = (px + s0) - gx;
+        const float fy = (py + s1) - gy;
+        // torch.maximum / np.maximum propagate NaN
+        const float occ = (isnan(locc) || isnan(s2)) ? NAN : fmaxf(locc, s2);
+        const float sig = sqrtf(lsig * lsig + s3 * s3);
+        const float score = (occ > a.occlusion_threshold) ? ninf : -sig;
+        const bool take = (k == 0) || (score > bscore) || (isnan(score) && !isnan(bscore));
+        if (take) {
+            bfx = fx; bfy = fy; bocc = occ; bsig = sig; bscore = score; bidx = k;
+        }
+    }
+    const float ex = gx + bfx, ey = gy + bfy;
+    if (ex < 0.0f || ey < 0.0f || ex >= static_cast<float>(a.W) || ey >= static_cast<float>(a.H)) bocc = 1.0f;
+    a.out[p] = bfx;
+    a.out[hw + p] = bfy;
+    a.out[2 * hw + p] = bocc;
+    a.out[3 * hw + p] = bsig;
+    if (a.index != nullptr) a.index[p] = static_cast<uint8_t>(bidx);
+}
+
+void launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream) {
+    const float sx = static_cast<float>(2.0 / (a.W - 1));
+    const float sy = static_cast<float>(2.0 / (a.H - 1));
+    dim3 grid((a.W + 255) / 256, a.H);
+    chain_select_kernel<<<grid, 256, 0, stream>>>(a, sx, sy);
+}
+
+// ==========================================================================================
+// warp_backward / chain / point sampling (MFT/results.py:87-188)
+// ==========================================================================================
+__device__ __forceinline__ float bilinear_zero_dev(const float* __restrict__ img, int H, int W, float ix, float iy) {
+    if (!(isfinite(ix) && isfinite(iy))) return NAN;
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wE = ix - x0f, wW = 1.0f - wE, wS = iy - y0f, wN = 1.0f - wS;
+    const int x0 = static_cast<int>(fminf(fmaxf(x0f, -2.0f), static_cast<float>(W + 1)));
+    const int y0 = static_cast<int>(fminf(fmaxf(y0f, -2.0f), static_cast<float>(H + 1)));
+    const bool xw = x0 >= 0 && x0 < W, xe = x0 + 1 >= 0 && x0 + 1 < W;
+    const bool yn = y0 >= 0 && y0 < H, ys = y0 + 1 >= 0 && y0 + 1 < H;
+    const long onw = static_cast<long>(y0) * W + x0;
+    const float vnw = (xw && yn) ? __ldg(img + onw) : 0.0f;
+    const float vne = (xe && yn) ? __ldg(img + onw + 1) : 0.0f;
+    const float vsw = (xw && ys) ? __ldg(img + onw + W) : 0.0f;
+    const float vse = (xe && ys) ? __ldg(img + onw + W + 1) : 0.0f;
+    float o = (wW * wN) * vnw;
+    o = o + (wE * wN) * vne;
+    o = o + (wW * wS) * vsw;
+    o = o + (wE * wS) * vse;
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+warp_backward_kernel(const float* __restrict__ flow, const float* __restrict__ img, int C, int H, int W, int add_flow,
+                     float* __restrict__ out, float sx, float sy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const long hw = static_cast<long>(H) * W, p = static_cast<long>(y) * W + x;
+    const float gx = static_cast<float>(x), gy = static_cast<float>(y);
+    const float px = gx + flow[p], py = gy + flow[hw + p];
+    const float ix = roundtrip_mul(px, sx, static_cast<float>(W - 1)), iy = roundtrip_mul(py, sy, static_cast<float>(H - 1));
+    for (int c = 0; c < C; ++c) {
+        float v = bilinear_zero_dev(img + c * hw, H, W, ix, iy);
+        if (add_flow) v = ((c == 0 ? px : py) + v) - (c == 0 ? gx : gy);
+        out[c * hw + p] = v;
+    }
+}
+
+void launch_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
+                          cudaStream_t stream) {
+    dim3 grid((W + 255) / 256, H);
+    warp_backward_kernel<<<grid, 256, 0, stream>>>(flow, img, C, H, W, add_flow, out, static_cast<float>(2.0 / (W - 1)),
+                                                   static_cast<float>(2.0 / (H - 1)));
+}
+
+__global__ void __launch_bounds__(256)
+sample_points_kernel(const float* __restrict__ field, int C, int H, int W, const float* __restrict__ pts, int N,
+                     int add_points, float* __restrict__ out, float sx, float sy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float px = pts[2 * i], py = pts[2 * i + 1];
+    const float ix = roundtrip_mul(px, sx, static_cast<float>(W - 1)), iy = roundtrip_mul(py, sy, static_cast<float>(H - 1));
+    const long hw = static_cast<long>(H) * W;
+    for (int c = 0; c < C; ++c) {
+        float v = bilinear_zero_dev(field + c * hw, H, W, ix, iy);
+        if (add_points && c < 2) v = (c == 0 ? px : py) + v;
+        out[static_cast<long>(c) * N + i] = v;
+    }
+}
+
+void launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
+                          float* out, cudaStream_t stream) {
+    if (N <= 0) return;
+    sample_points_kernel<<<(N + 255) / 256, 256, 0, stream>>>(field, C, H, W, points_xy, N, add_points, out,
+                                                              static_cast<float>(2.0 / (W - 1)),
+                                                              static_cast<float>(2.0 / (H - 1)));
+}
+
+// ==========================================================================================
+// frame -> im2col patches for the 7x7/2 first conv (MFT/raft.py:41-48, core/raft.py:122-124)
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+frame_patches_kernel(const uint8_t* __restrict__ bgr, int H, int W, int Hp, int Wp, int pl, int pt,
+                     __half* __restrict__ patches, long total) {
+    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k = static_cast<int>(i % 152);
+    const long op = i / 152;
+    const int Wo = Wp / 2;
+    const int oy = static_cast<int>(op / Wo), ox = static_cast<int>(op % Wo);
+    float v = 0.0f;
+    if (k < 147) {
+        const int c = k % 3, kx = (k / 3) % 7, ky = k / 21;
+        const int yp = 2 * oy + ky - 3, xp = 2 * ox + kx - 3;
+        if (yp >= 0 && yp < Hp && xp >= 0 && xp < Wp) {
+            const int ys = min(max(yp - pt, 0), H - 1), xs = min(max(xp - pl, 0), W - 1);
+            const float u = static_cast<float>(bgr[(static_cast<long>(ys) * W + xs) * 3 + (2 - c)]);
+            v = 2.0f * (u / 255.0f) - 1.0f;
+        }
+    }
+    patches[i] = __float2half_rn(v);
+}
+
+void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
+                          cudaStream_t stream) {
+    const long total = static_cast<long>(Hp / 2) * (Wp / 2) * 152;
+    frame_patches_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(bgr, H, W, Hp, Wp, pad_left,
+                                                                                         pad_top, patches, total);
+}
+
+// ==========================================================================================
+// instance norm (MFT/RAFT/core/extractor.py:28-32,129-130: biased variance, eps 1e-5, no affine)
+// ==========================================================================================
+constexpr int kStatThreads = 192;   // divisible by C/2 for C in {64, 96, 128}
+
+__global__ void __launch_bounds__(kStatThreads)
+instnorm_stats_kernel(const __half* __restrict__ raw, int P, int C, int pix_per_block, double* __restrict__ sums) {
+    __shared__ float red[2][kStatThreads * 2];
+    const int b = blockIdx.y;
+    const int c2 = C / 2;
+    const int cp = threadIdx.x % c2, pl = threadIdx.x / c2, nrow = kStatThreads / c2;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const __half2* src = reinterpret_cast<const __half2*>(raw + static_cast<long>(b) * P * C);
+    for (int p = p0 + pl; p < p1; p += nrow) {
+        const float2 v = __half22float2(src[static_cast<long>(p) * c2 + cp]);
+        s0 += v.x; s1 += v.y;
+        q0 += v.x * v.x; q1 += v.y * v.y;
+    }
+    red[0][threadIdx.x * 2] = s0; red[0][threadIdx.x * 2 + 1] = s1;
+    red[1][threadIdx.x * 2] = q0; red[1][threadIdx.x * 2 + 1] = q1;
+    __syncthreads();
+    if (pl == 0) {
+        for (int r = 1; r < nrow; ++r) {
+            const int t = r * c2 + cp;
+            s0 += red[0][t * 2]; s1 += red[0][t * 2 + 1];
+            q0 += red[1][t * 2]; q1 += red[1][t * 2 + 1];
+        }
+        double* o = sums + static_cast<long>(b) * 2 * C;
+        atomicAdd(o + 2 * cp, static_cast<double>(s0));
+        atomicAdd(o + 2 * cp + 1, static_cast<double>(s1));
+        atomicAdd(o + C + 2 * cp, static_cast<double>(q0));
+        atomicAdd(o + C + 2 * cp + 1, static_cast<double>(q1));
+    }
+}
+
+void launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums, cudaStream_t stream) {
+    cudaMemsetAsync(sums, 0, sizeof(double) * B * 2 * C, stream);
+    const int pix_per_block = 256;
+    dim3 grid((P + pix_per_block - 1) / pix_per_block, B);
+    instnorm_stats_kernel<<<grid, kStatThreads, 0, stream>>>(raw, P, C, pix_per_block, sums);
+}
+
+__global__ void __launch_bounds__(256)
+instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict__ sums, int P, int C, int relu,
+                      const __half2* __restrict__ res, __half2* __restrict__ out, long total2) {
+    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total2) return;
+    const int c2 = C / 2;
+    const int cp = static_cast<int>(i % c2);
+    const int b = static_cast<int>(i / (static_cast<long>(P) * c2));
+    const double* s = sums + static_cast<long>(b) * 2 * C;
+    const double inv = 1.0 / P;
+    const double m0 = s[2 * cp] * inv, m1 = s[2 * cp + 1] * inv;
+    const double v0 = fmax(s[C + 2 * cp] * inv - m0 * m0, 0.0), v1 = fmax(s[C + 2 * cp + 1] * inv - m1 * m1, 0.0);
+    const float r0 = static_cast<float>(1.0 / sqrt(v0 + 1e-5)), r1 = static_cast<float>(1.0 / sqrt(v1 + 1e-5));
+    const float2 x = __half22float2(raw[i]);
+    float y0 = (x.x - static_cast<float>(m0)) * r0, y1 = (x.y - static_cast<float>(m1)) * r1;
+    if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+    if (res != nullptr) {
+        const float2 r = __half22float2(res[i]);
+        y0 = fmaxf(y0 + r.x, 0.f);
+        y1 = fmaxf(y1 + r.y, 0.f);
+    }
+    out[i] = __floats2half2_rn(y0, y1);
+}
+
+void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
+                           __half* out, cudaStream_t stream) {
+    const long total2 = static_cast<long>(B) * P * C / 2;
+    instnorm_apply_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __half2*>(raw), sums, P, C, relu, reinterpret_cast<const __half2*>(res),
+        reinterpret_cast<__half2*>(out), total2);
+}
+
+// ==========================================================================================
+// per-pair state set-up (core/raft.py:141-154): gather cached per-frame features, net/inp split,
+// coords1 = coords0 = grid
+// ==========================================================================================
+__global__ void __launch_bounds__(128)
+pair_setup_kernel(const PairSetup a) {
+    const int npx = a.h * a.w;
+    const long pp = blockIdx.x;                 // pair * npx + n
+    const int pair = static_cast<int>(pp / npx), n = static_cast<int>(pp % npx);
+    const int ls = a.slots[2 * pair], rs = a.slots[2 * pair + 1];
+    const int t = threadIdx.x;                  // 128 threads
+    // fmaps: 256 halves = 128 half2 per pixel
+    reinterpret_cast<__half2*>(a.F1)[pp * 128 + t] =
+        reinterpret_cast<const __half2*>(a.fmap_slots)[(static_cast<long>(ls) * npx + n) * 128 + t];
+    reinterpret_cast<__half2*>(a.F2)[pp * 128 + t] =
+        reinterpret_cast<const __half2*>(a.fmap_slots)[(static_cast<long>(rs) * npx + n) * 128 + t];
+    const float hv = a.net_slots[(static_cast<long>(ls) * npx + n) * 128 + t];
+    a.h32[pp * 128 + t] = hv;
+    a.X[pp * 512 + t] = __float2half_rn(hv);
+    a.X[pp * 512 + 128 + t] = a.inp_slots[(static_cast<long>(ls) * npx + n) * 128 + t];
+    if (t < 2) a.coords1[pp * 2 + t] = static_cast<float>(t == 0 ? n % a.w : n / a.w);
+}
+
+void launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
+    pair_setup_kernel<<<static_cast<unsigned>(static_cast<long>(a.n_pairs) * a.h * a.w), 128, 0, stream>>>(a);
+}
+
+// ==========================================================================================
+// correlation pyramid pooling (core/corr.py:26-28): avg_pool2d(2, stride 2), floor sizes
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+corr_pool_kernel(const float* __restrict__ L0, float* __restrict__ L1, float* __restrict__ L2, float* __restrict__ L3,
+                 int h, int w) {
+    extern __shared__ float sm[];
+    const int h1 = h / 2, w1 = w / 2, h2 = h1 / 2, w2 = w1 / 2, h3 = h2 / 2, w3 = w2 / 2;
+    float* s1 = sm;
+    float* s2 = sm + h1 * w1;
+    const long row = blockIdx.x;
+    const float* src = L0 + row * h * w;
+    for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
+        const int y = i / w1, x = i % w1;
+        const float* q = src + (2 * y) * w + 2 * x;
+        const float v = (((q[0] + q[1]) + q[w]) + q[w + 1]) * 0.25f;
+        s1[i] = v;
+        L1[row * h1 * w1 + i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
+        const int y = i / w2, x = i % w2;
+        const float* q = s1 + (2 * y) * w1 + 2 * x;
+        const float v = (((q[0] + q[1]) + q[w1]) + q[w1 + 1]) * 0.25f;
+        s2[i] = v;
+        L2[row * h2 * w2 + i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h3 * w3; i += blockDim.x) {
+        const int y = i / w3, x = i % w3;
+        const float* q = s2 + (2 * y) * w2 + 2 * x;
+        L3[row * h3 * w3 + i] = (((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f;
+    }
+}
+
+void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long rows, int h, int w, cudaStream_t stream) {
+    const size_t smem = sizeof(float) * (static_cast<size_t>(h / 2) * (w / 2) + static_cast<size_t>(h / 4) * (w / 4));
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    corr_pool_kernel<<<static_cast<unsigned>(rows), 256, smem, stream>>>(L0, L1, L2, L3, h, w);
+}
+
+// ==========================================================================================
+// pyramid lookup (core/corr.py:30-51) + flow operands of the motion encoder
+// one warp per (pair, source pixel)
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+lookup_kernel(const LookupArgs a) {
+    const int npx = a.h * a.w;
+    const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (pp >= static_cast<long>(a.n_pairs) * npx) return;
+    const int lane = threadIdx.x & 31;
+    const int n = static_cast<int>(pp % npx);
+    const int y = n / a.w, x = n % a.w;
+    const float cx = a.coords1[pp * 2], cy = a.coords1[pp * 2 + 1];
+    __half* out = a.corr16 + pp * 328;
+    int hl = a.h, wl = a.w;
+    float div = 1.0f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
+        const float lx = cx / div, ly = cy / div;
+        const float wm1 = static_cast<float>(wl - 1), hm1 = static_cast<float>(hl - 1);
+        for (int o = lane; o < 81; o += 32) {
+            const int i = o / 9, j = o - i * 9;          // i: x offset index, j: y offset index
+            const float ix = roundtrip_div(lx + static_cast<float>(i - 4), wm1);
+            const float iy = roundtrip_div(ly + static_cast<float>(j - 4), hm1);
+            float r;
+            if (!(isfinite(ix) && isfinite(iy))) {
+                r = NAN;
+            } else {
+                const float x0f = floorf(ix), y0f = floorf(iy);
+                const float wE = ix - x0f, wW = 1.0f - wE, wS = iy - y0f, wN = 1.0f - wS;
+                const int x0 = static_cast<int>(fminf(fmaxf(x0f, -2.0f), static_cast<float>(wl + 1)));
+                const int y0 = static_cast<int>(fminf(fmaxf(y0f, -2.0f), static_cast<float>(hl + 1)));
+                const bool xw = x0 >= 0 && x0 < wl, xe = x0 + 1 >= 0 && x0 + 1 < wl;
+                const bool yn = y0 >= 0 && y0 < hl, ys = y0 + 1 >= 0 && y0 + 1 < hl;
+                const long onw = static_cast<long>(y0) * wl + x0;
+                const float vnw = (xw && yn) ? __ldg(base + onw) : 0.0f;
+                const float vne = (xe && yn) ? __ldg(base + onw + 1) : 0.0f;
+                const float vsw = (xw && ys) ? __ldg(base + onw + wl) : 0.0f;
+                const float vse = (xe && ys) ? __ldg(base + onw + wl + 1) : 0.0f;
+                r = (wW * wN) * vnw;
+                r = r + (wE * wN) * vne;
+                r = r + (wW * wS) * vsw;
+                r = r + (wE * wS) * vse;
+            }
+            out[l * 81 + o] = __float2half_rn(r);
+        }
+        hl >>= 1; wl >>= 1; div *= 2.0f;
+    }
+    if (lane < 4) out[324 + lane] = __float2half_rn(0.0f);
+    // flow = coords1 - coords0 (core/raft.py:179); 7x7x2 zero-padded neighbourhood for convf1
+    const long pbase = pp - n;
+    __half* fp = a.flowpatch16 + pp * 104;
+    for (int k = lane; k < 104; k += 32) {
+        float v = 0.0f;
+        if (k < 98) {
+            const int c = k & 1, kx = (k >> 1) % 7, ky = (k >> 1) / 7;
+            const int yy = y + ky - 3, xx = x + kx - 3;
+            if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
+                v = a.coords1[(pbase + static_cast<long>(yy) * a.w + xx) * 2 + c] - static_cast<float>(c == 0 ? xx : yy);
+        }
+        fp[k] = __float2half_rn(v);
+    }
+    if (lane < 2) a.X[pp * 512 + 382 + lane] = __float2half_rn((lane == 0 ? cx : cy) - static_cast<float>(lane == 0 ? x : y));
+}
+
+void launch_lookup(const LookupArgs& a, cudaStream_t stream) {
+    const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
+    lookup_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(a);
+}
+
+// ==========================================================================================
+// OU head input: [net | inp | corr | flow | delta_flow | motion] = 712 channels (update.py:197)
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+ou_pack_kernel(const OuPackArgs a) {
+    const int npx = a.h * a.w;
+    const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (pp >= static_cast<long>(a.n_pairs) * npx) return;
+    const int lane = threadIdx.x & 31;
+    const int n = static_cast<int>(pp % npx);
+    const __half* X = a.X + pp * 512;
+    const __half* C = a.corr16 + pp * 328;
+    __half* o = a.packed + pp * 720;
+    for (int k = lane; k < 720; k += 32) {
+        __half v;
+        if (k < 256) v = X[k];
+        else if (k < 580) v = C[k - 256];
+        else if (k < 582) v = __float2half_rn(a.coords1[pp * 2 + (k - 580)] - static_cast<float>(k == 580 ? n % a.w : n / a.w));
+        else if (k < 584) v = __float2half_rn(a.delta32[pp * 2 + (k - 582)]);
+        else if (k < 712) v = X[256 + (k - 584)];
+        else v = __float2half_rn(0.0f);
+        o[k] = v;
+    }
+}
+
+void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
+    const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
+    ou_pack_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(a);
+}
+
+// ==========================================================================================
+// convex 8x upsampling of flow / occlusion logits / uncertainty with one shared mask
+// (core/raft.py:83-94,190-218) + post-processing and unpadding (MFT/raft.py:56-62)
+// 64 threads per coarse pixel (one per 8x8 sub-position), 4 coarse pixels per block
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+upsample_kernel(const UpsampleArgs a) {
+    const int npx = a.h * a.w;
+    const long pp = static_cast<long>(blockIdx.x) * 4 + (threadIdx.x >> 6);
+    if (pp >= static_cast<long>(a.n_pairs) * npx) return;
+    const int sub = threadIdx.x & 63;
+    const int sy = sub >> 3, sx = sub & 7;
+    const int pair = static_cast<int>(pp / npx), n = static_cast<int>(pp % npx);
+    const int y = n / a.w, x = n % a.w;
+    const float* m = a.mask32 + pp * 576 + sub;
+    float mk[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        mk[k] = m[k * 64];
+        mx = fmaxf(mx, mk[k]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        mk[k] = expf(mk[k] - mx);
+        den += mk[k];
+    }
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const long pbase = pp - n;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        if (yy < 0 || yy >= a.h || xx < 0 || xx >= a.w) continue;
+        const long q = pbase + static_cast<long>(yy) * a.w + xx;
+        const float wk = mk[k] / den;
+        const float2 c = *reinterpret_cast<const float2*>(a.coords1 + q * 2);
+        const float4 ou = *reinterpret_cast<const float4*>(a.ou32 + q * 4);
+        acc[0] += wk * (8.0f * (c.x - static_cast<float>(xx)));
+        acc[1] += wk * (8.0f * (c.y - static_cast<float>(yy)));
+        acc[2] += wk * ou.x;
+        acc[3] += wk * ou.y;
+        acc[4] += wk * ou.z;
+    }
+    const int Y = 8 * y + sy - a.pad_top, Xo = 8 * x + sx - a.pad_left;
+    if (Y < 0 || Y >= a.H || Xo < 0 || Xo >= a.W) return;
+    const long hw = static_cast<long>(a.H) * a.W;
+    float* o = a.out + static_cast<long>(pair) * 4 * hw + static_cast<long>(Y) * a.W + Xo;
+    o[0] = acc[0];
+    o[hw] = acc[1];
+    const float lm = fmaxf(acc[2], acc[3]);
+    const float e0 = expf(acc[2] - lm), e1 = expf(acc[3] - lm);
+    o[2 * hw] = e1 / (e0 + e1);
+    o[3 * hw] = sqrtf(expf(acc[4]));
+}
+
+void launch_upsample(const UpsampleArgs& a, cudaStream_t stream) {
+    const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
+    upsample_kernel<<<static_cast<unsigned>((total + 3) / 4), 256, 0, stream>>>(a);
+}
+
+}  // namespace mftb

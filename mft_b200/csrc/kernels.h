@@ -1,0 +1,88 @@
+// Bandwidth-bound kernels of the MFT hot path (everything that is not an implicit GEMM).
+// Host-callable launchers; all pointers are device pointers; all launches go to `stream`.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace mftb {
+
+constexpr int kMaxChains = 8;
+
+struct ChainSelectArgs {
+    const float* left[kMaxChains];   // template->left results, planar (4,H,W) = fx, fy, occlusion, sigma
+    const float* right;              // left->current flows, planar (K,4,H,W)
+    float* out;                      // selected template->current result, planar (4,H,W)
+    uint8_t* index;                  // selected chain per pixel (H,W); may be nullptr
+    int K, H, W;
+    float occlusion_threshold;
+};
+void launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream);
+
+// FlowOUTrackingResult.warp_backward (MFT/results.py:116-136): out[c,y,x] = bilinear(img[c], (x,y)+flow[:,y,x]),
+// zeros outside, align_corners=True, same defined operation order as chain_select.  add_flow=1 turns it into
+// FlowOUTrackingResult.chain (results.py:87-114) for C == 2: out = (p + S) - grid.
+void launch_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
+                          cudaStream_t stream);
+
+// Bilinear point queries (MFT/results.py:138-188, MFT/utils/interpolation.py:76-94): out[c, i] =
+// bilinear(field[c], points[i]) (+ points[i][c] when add_points, i.e. warp_forward_points).
+void launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
+                          float* out, cudaStream_t stream);
+
+// uint8 BGR HWC frame -> fp16 im2col patches of the encoders' 7x7 stride-2 first conv,
+// [ (Hp/2)*(Wp/2) ][152], k = (ky*7+kx)*3 + c (c: R,G,B), values 2*(v/255)-1; the frame is
+// replicate-padded to Hp x Wp (pad_left/pad_top) first, the conv itself zero-pads.
+void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
+                          cudaStream_t stream);
+
+// Instance norm over raw fp16 conv outputs [B][P][C].
+void launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums /*[B][2][C], zeroed here*/,
+                           cudaStream_t stream);
+// out = act((raw-mean)*rstd); if res != nullptr: out = relu(res + out).  act = relu if relu else identity.
+void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
+                           __half* out, cudaStream_t stream);
+
+struct PairSetup {
+    const int* slots;                // device int[2*n_pairs]: (left, right) feature-slot per pair
+    const __half* fmap_slots;        // [slot][Npx][256]
+    const float* net_slots;          // [slot][Npx][128]
+    const __half* inp_slots;         // [slot][Npx][128]
+    __half* F1; __half* F2;          // [pair][Npx][256]
+    float* h32;                      // [pair][Npx][128]
+    __half* X;                       // [pair][Npx][512]  h | inp | motion | r*h
+    float* coords1;                  // [pair][Npx][2]
+    int n_pairs, h, w;
+};
+void launch_pair_setup(const PairSetup& a, cudaStream_t stream);
+
+// 2x2 average pooling of the correlation volume over the target dims: L0 [rows][h*w] -> L1..L3.
+void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long rows, int h, int w, cudaStream_t stream);
+
+struct LookupArgs {
+    const float* lvl[4];             // pyramid levels [pair*Npx + n][h_l*w_l]
+    const float* coords1;            // [pair][Npx][2]
+    __half* corr16;                  // [pair*Npx][328]  (324 used)
+    __half* flowpatch16;             // [pair*Npx][104]  (98 used): 7x7x2 neighbourhood of the flow
+    __half* X;                       // writes flow into X[:, 382:384]
+    int n_pairs, h, w;
+};
+void launch_lookup(const LookupArgs& a, cudaStream_t stream);
+
+struct OuPackArgs {
+    const __half* X; const __half* corr16; const float* coords1; const float* delta32;
+    __half* packed;                  // [pair*Npx][720]
+    int n_pairs, h, w;
+};
+void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream);
+
+struct UpsampleArgs {
+    const float* mask32;             // [pair*Npx][576]
+    const float* coords1;            // [pair*Npx][2]
+    const float* ou32;               // [pair*Npx][4]: occlusion logit0, logit1, uncertainty, pad
+    float* out;                      // planar (pairs,4,H,W): fx, fy, occlusion prob, sigma
+    int n_pairs, h, w, H, W, pad_left, pad_top;
+};
+void launch_upsample(const UpsampleArgs& a, cudaStream_t stream);
+
+}  // namespace mftb

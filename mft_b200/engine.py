@@ -1,0 +1,125 @@
+"""Python handle on the native engine (libmft_b200.so).  torch is used for device memory and
+streams only; every computation is a kernel of the library."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, weights as _weights
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One engine = one set of uploaded weights + one frame geometry on the current device."""
+
+    def __init__(self, state_dict):
+        if not torch.cuda.is_available():
+            raise _lib.MftB200Error('mft_b200 needs a CUDA device (B200); there is no CPU fallback')
+        self.L = _lib.lib()
+        ctx = C.c_void_p()
+        _lib.check(self.L.mftb200_create(C.byref(ctx)))
+        self.ctx = ctx
+        self.geometry = None
+        W = _weights.strip_module_prefix(state_dict)
+        for i, (w16, bias, cout_pad, ktot, bias_len) in enumerate(_weights.pack_all(W)):
+            w16 = np.ascontiguousarray(w16)
+            bias = np.ascontiguousarray(bias)
+            _lib.check(self.L.mftb200_upload_layer(self.ctx, i, w16.ctypes.data, bias.ctypes.data, cout_pad, ktot,
+                                                   bias_len), self.ctx)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'ctx', None):
+                self.L.mftb200_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------
+    def configure(self, H, W, max_pairs=7, n_slots=34, iters=12):
+        geo = (H, W, max_pairs, n_slots, iters)
+        if self.geometry != geo:
+            _lib.check(self.L.mftb200_configure(self.ctx, H, W, max_pairs, n_slots, iters), self.ctx)
+            self.geometry = geo
+            self._pinned = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        return self
+
+    def set_option(self, key, value):
+        _lib.check(self.L.mftb200_set_option(self.ctx, key.encode(), int(value)), self.ctx)
+
+    def encode_frame(self, frame, slot):
+        """frame: (H,W,3) uint8 BGR numpy array (host) or torch CUDA tensor."""
+        H, W = self.geometry[:2]
+        if isinstance(frame, torch.Tensor) and frame.is_cuda:
+            assert frame.dtype == torch.uint8 and tuple(frame.shape) == (H, W, 3) and frame.is_contiguous()
+            _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(frame.data_ptr()), 1, slot, _stream_ptr()), self.ctx)
+            return
+        frame = np.asarray(frame)
+        assert frame.dtype == np.uint8 and frame.shape == (H, W, 3), (frame.dtype, frame.shape)
+        # stage through pinned memory so the H2D copy is asynchronous w.r.t. the host
+        torch.cuda.current_stream().synchronize()
+        self._pinned.numpy()[...] = frame
+        _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(self._pinned.data_ptr()), 0, slot, _stream_ptr()), self.ctx)
+
+    def refine(self, left_slots, right_slots, out=None):
+        """Batched RAFT-OU refinement.  Returns CUDA float tensor (n_pairs, 4, H, W)."""
+        H, W = self.geometry[:2]
+        n = len(left_slots)
+        assert n == len(right_slots) and 1 <= n <= self.geometry[2]
+        if out is None:
+            out = torch.empty((n, 4, H, W), dtype=torch.float32, device='cuda')
+        ls = (C.c_int * n)(*[int(s) for s in left_slots])
+        rs = (C.c_int * n)(*[int(s) for s in right_slots])
+        _lib.check(self.L.mftb200_raft_refine(self.ctx, n, ls, rs, C.c_void_p(out.data_ptr()), _stream_ptr()), self.ctx)
+        return out
+
+    def check_device(self):
+        _lib.check(self.L.mftb200_device_error_flag(self.ctx), self.ctx)
+
+    def launch_count(self):
+        return int(self.L.mftb200_launch_count(self.ctx))
+
+    def debug_buffer(self, name, dtype, shape):
+        """Copy of (the head of) a named internal buffer as a torch CUDA tensor."""
+        n = int(np.prod(shape))
+        out = torch.empty(n, dtype=dtype, device='cuda')
+        torch.cuda.synchronize()
+        _lib.check(self.L.mftb200_debug_read(self.ctx, name.encode(), C.c_void_p(out.data_ptr()),
+                                             n * out.element_size()), self.ctx)
+        return out.reshape(shape)
+
+
+def chain_select(lefts, right, occlusion_threshold, want_index=True):
+    """Fused flow-chain composition + per-pixel best-chain selection + invalid mask.
+
+    lefts: list of K CUDA float tensors (4,H,W) (template -> left_k), right: (K,4,H,W)
+    (left_k -> current).  Candidate order must be [inf, ascending delta].  Returns
+    (result (4,H,W), index uint8 (H,W) or None)."""
+    L = _lib.lib()
+    K = len(lefts)
+    assert right.is_cuda and right.dtype == torch.float32 and right.is_contiguous() and right.shape[0] == K
+    _, _, H, W = right.shape
+    for t in lefts:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (4, H, W)
+    out = torch.empty((4, H, W), dtype=torch.float32, device=right.device)
+    idx = torch.empty((H, W), dtype=torch.uint8, device=right.device) if want_index else None
+    ptrs = (C.c_void_p * K)(*[t.data_ptr() for t in lefts])
+    _lib.check(L.mftb200_chain_select(K, ptrs, C.c_void_p(right.data_ptr()), float(occlusion_threshold), H, W,
+                                      C.c_void_p(out.data_ptr()), C.c_void_p(idx.data_ptr() if want_index else None),
+                                      _stream_ptr()))
+    return out, idx
+
+
+def conv2d_test(x16, w16, bias, cin, cout_pad, n_tile, kh, kw, stride, relu, impl):
+    """Unit-test hook: x16 CUDA fp16 (B,H,W,pitch); w16 CUDA fp16 [cout_pad][ktot]; returns fp32 (B,Ho,Wo,cout_pad)."""
+    L = _lib.lib()
+    B, H, W, pitch = x16.shape
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    out = torch.zeros((B, Ho, Wo, cout_pad), dtype=torch.float32, device='cuda')
+    _lib.check(L.mftb200_conv2d_test(C.c_void_p(x16.data_ptr()), B, H, W, pitch, cin, C.c_void_p(w16.data_ptr()),
+                                     C.c_void_p(bias.data_ptr()), cout_pad, n_tile, kh, kw, stride, int(relu),
+                                     C.c_void_p(out.data_ptr()), int(impl), _stream_ptr()))
+    return out
