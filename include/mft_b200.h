@@ -87,7 +87,8 @@ int mftb200_sample_points(const float* field, int C, int H, int W, const float* 
 
 /* ---- diagnostics / test hooks ---------------------------------------------------------------- */
 int mftb200_device_error_flag(mftb200_ctx* ctx);          /* syncs; 0 = clean */
-/* key "conv_impl": 0 = tcgen05 (product), 1 = SIMT cross-check kernel (tests only). */
+/* keys: "conv_impl" 0 = tcgen05 (product), 1 = SIMT cross-check kernel (tests only); "iters" = GRU
+ * iterations; "profile" 0|1 = per-launch event timing (see mftb200_profile_fetch). */
 int mftb200_set_option(mftb200_ctx* ctx, const char* key, int value);
 /* Named internal buffer for stage-level parity tests ("fmap_slots", "net_slots", "corr_l0", ...). */
 int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t* bytes);
@@ -95,6 +96,11 @@ int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t*
 int mftb200_debug_read(mftb200_ctx* ctx, const char* name, void* dst_device, size_t bytes);
 /* Number of kernels launched by this context since creation (bench's gpu_launches). */
 long long mftb200_launch_count(const mftb200_ctx* ctx);
+
+/* With option "profile"=1 every launch step is bracketed by CUDA events on its stream.  Fetch (and
+ * clear) the accumulated device time: index 0 = tensor-core conv/GEMM launches, 1 = the
+ * bandwidth-bound kernels.  Used by bench.py for the live roofline numbers. */
+int mftb200_profile_fetch(mftb200_ctx* ctx, double* ms_by_kind /*[2]*/, long long* steps_by_kind /*[2]*/);
 
 /* Stand-alone convolution through the product kernel, for unit tests: x fp16 NHWC
  * (B,H,W,pitch) view of `cin` channels, packed weights as in upload_layer, taps = kh x kw

@@ -36,6 +36,7 @@ def _declare(lib):
         'mftb200_set_option': (ci, [vp, C.c_char_p, ci]),
         'mftb200_debug_buffer': (ci, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         'mftb200_debug_read': (ci, [vp, C.c_char_p, vp, C.c_size_t]),
+        'mftb200_profile_fetch': (ci, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
         'mftb200_launch_count': (C.c_longlong, [vp]),
         'mftb200_conv2d_test': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     }

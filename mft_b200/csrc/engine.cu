@@ -74,8 +74,18 @@ struct mftb200_ctx {
     size_t corr_bytes[4] = {0, 0, 0, 0};
 
     std::vector<ConvPlan> plans;
-    using Step = std::function<const char*(mftb200_ctx*, cudaStream_t)>;
+    struct Step {
+        std::function<const char*(mftb200_ctx*, cudaStream_t)> fn;
+        int kind = 1;                       // 0 = tensor-core conv / GEMM launch, 1 = bandwidth-bound kernel(s)
+        Step() = default;
+        template <class F>
+        Step(F f, int k = 1) : fn(std::move(f)), kind(k) {}
+    };
     std::vector<Step> enc_steps, pre_steps, iter_steps, final_steps;
+    // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_events;   // pairs
+    std::vector<int> prof_kinds;
     int cur_slot = 0, cur_pairs = 0;
 
     int fail(int code, const char* fmt, ...) {
@@ -152,10 +162,10 @@ struct Builder {
 };
 
 mftb200_ctx::Step conv_step(int plan_idx, bool batched_pairs) {
-    return [plan_idx, batched_pairs](mftb200_ctx* c, cudaStream_t s) -> const char* {
+    return mftb200_ctx::Step([plan_idx, batched_pairs](mftb200_ctx* c, cudaStream_t s) -> const char* {
         c->launches++;
         return conv_launch(c->plans[plan_idx], batched_pairs ? c->cur_pairs : 1, s, c->conv_impl);
-    };
+    }, 0);
 }
 
 const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
@@ -229,7 +239,7 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
             ConvEpi& e = B.epi(i);
             e.n_valid = 256; e.out16_stride = 256;
         }
-        S.push_back([i, inorm](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        S.push_back(mftb200_ctx::Step([i, inorm](mftb200_ctx* cc, cudaStream_t s) -> const char* {
             ConvPlan p = cc->plans[i];
             const size_t off = static_cast<size_t>(cc->cur_slot) * cc->npx;
             if (inorm) {
@@ -240,7 +250,7 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
             }
             cc->launches++;
             return conv_launch(p, 1, s, cc->conv_impl);
-        });
+        }, 0));
     }
     return B.err;
 }
@@ -363,7 +373,20 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
 
 int run_steps(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cudaStream_t s) {
     for (auto& st : steps) {
-        if (const char* e = st(c, s)) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+        if (c->profile) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, s);
+            const char* e = st.fn(c, s);
+            cudaEventRecord(b, s);
+            c->prof_events.push_back(a);
+            c->prof_events.push_back(b);
+            c->prof_kinds.push_back(st.kind);
+            if (e) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+        } else if (const char* e = st.fn(c, s)) {
+            return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+        }
     }
     return MFTB200_OK;
 }
@@ -597,10 +620,30 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (!c || !key) return MFTB200_ERR_ARG;
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
+    if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     return c->fail(MFTB200_ERR_ARG, "set_option: unknown key %s", key);
 }
 
 long long mftb200_launch_count(const mftb200_ctx* c) { return c ? c->launches : 0; }
+
+int mftb200_profile_fetch(mftb200_ctx* c, double* ms_by_kind, long long* steps_by_kind) {
+    if (!c || !ms_by_kind || !steps_by_kind) return MFTB200_ERR_ARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return c->fail(MFTB200_ERR_CUDA, "profile_fetch: device error");
+    ms_by_kind[0] = ms_by_kind[1] = 0.0;
+    steps_by_kind[0] = steps_by_kind[1] = 0;
+    for (size_t i = 0; i < c->prof_kinds.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]);
+        const int k = c->prof_kinds[i] ? 1 : 0;
+        ms_by_kind[k] += ms;
+        steps_by_kind[k] += 1;
+        cudaEventDestroy(c->prof_events[2 * i]);
+        cudaEventDestroy(c->prof_events[2 * i + 1]);
+    }
+    c->prof_events.clear();
+    c->prof_kinds.clear();
+    return MFTB200_OK;
+}
 
 int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* bytes) {
     if (!c || !name || !ptr || !bytes) return MFTB200_ERR_ARG;

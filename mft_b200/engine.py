@@ -79,6 +79,13 @@ class Engine:
     def check_device(self):
         _lib.check(self.L.mftb200_device_error_flag(self.ctx), self.ctx)
 
+    def profile_fetch(self):
+        """(ms, steps) per kind: index 0 = tensor-core conv launches, 1 = bandwidth-bound kernels."""
+        ms = (C.c_double * 2)()
+        n = (C.c_longlong * 2)()
+        _lib.check(self.L.mftb200_profile_fetch(self.ctx, ms, n), self.ctx)
+        return [float(ms[0]), float(ms[1])], [int(n[0]), int(n[1])]
+
     def launch_count(self):
         return int(self.L.mftb200_launch_count(self.ctx))
 

@@ -1,0 +1,80 @@
+"""RAFTWrapper with the reference's module surface (MFT/raft.py of serycjon/MFT), backed by the
+native engine.  compute_flow(src, dst, mode='flow') -> flow (2,H,W), {'occlusion','sigma','debug'}.
+
+Unlike the reference, the per-frame encoders and the pair refinement are separate engine calls
+(encode_frame / refine) so that the tracker encodes every frame once and batches all of a
+frame's delta pairs into one refinement (SURVEY.md TL;DR: 21 encoder passes -> 2 per frame)."""
+import logging
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import weights as _weights
+from .engine import Engine
+
+logger = logging.getLogger(__name__)
+
+MAX_PAIRS = 7          # pairs per batched refinement (the 7 delta chains of configs/MFT_cfg.py)
+TRACKER_SLOTS = 34     # template + 32 past frames + current (MFT.cleanup_memory keeps max-delta frames)
+N_SLOTS = TRACKER_SLOTS + 2   # + two scratch slots for stand-alone compute_flow calls
+
+
+class RAFTWrapper:
+    def __init__(self, config):
+        """config: flow config with .model (checkpoint path, or a state dict), .flow_iters,
+        .raft_params (must describe the shipped architecture: non-small, separate OU heads)."""
+        self.C = config
+        params = getattr(config, 'raft_params', None)
+        if params:
+            small = params.get('small', False) if isinstance(params, dict) else getattr(params, 'small', False)
+            occl = params.get('occlusion_module', None) if isinstance(params, dict) else getattr(params, 'occlusion_module', None)
+            if small or occl != 'separate_with_uncertainty':
+                raise NotImplementedError('mft_b200 implements the shipped RAFT-OU architecture only '
+                                          "(small=False, occlusion_module='separate_with_uncertainty')")
+        model = config.model
+        state = model if isinstance(model, dict) else _weights.load_checkpoint(str(model))
+        self.iters = int(config.flow_iters) if config.flow_iters else 12
+        self.engine = Engine(state)
+        self.model = self.engine          # the reference exposes the network as .model (raft.py:28)
+        self.last_flow_shape = None
+
+    def ensure_geometry(self, H, W):
+        self.engine.configure(H, W, max_pairs=MAX_PAIRS, n_slots=N_SLOTS, iters=self.iters)
+        return self.engine
+
+    def compute_flow(self, src_img, dst_img, mode='TC', vis=False, src_img_identifier=None,
+                     numpy_out=False, init_flow=None, vis_debug=False):
+        """src_img, dst_img: (H,W,3) uint8 BGR.  mode 'flow' or 'TC' (raft.py:30-94)."""
+        if init_flow is not None:
+            raise NotImplementedError('init_flow is never used by the tracker (MFT.py:98) and is not supported')
+        H, W = src_img.shape[:2]
+        eng = self.ensure_geometry(H, W)
+        eng.encode_frame(src_img, TRACKER_SLOTS)
+        eng.encode_frame(dst_img, TRACKER_SLOTS + 1)
+        out = eng.refine([TRACKER_SLOTS], [TRACKER_SLOTS + 1])[0]
+        flow, occlusions, sigma = out[0:2], out[2:3], out[3:4]
+        extra = {'occlusion': occlusions, 'sigma': sigma, 'debug': None}
+        if mode == 'flow':
+            if numpy_out:
+                flow = flow.cpu().numpy()
+                extra['occlusion'] = occlusions.cpu().numpy()
+                extra['sigma'] = sigma.cpu().numpy()
+            return flow, extra
+        if mode == 'TC':
+            self.last_flow_shape = {'delta': 2, 'H': H, 'W': W}
+            ys, xs = torch.meshgrid(torch.arange(H, device=flow.device), torch.arange(W, device=flow.device), indexing='ij')
+            src = torch.stack([xs.reshape(-1), ys.reshape(-1)], 0)
+            dst = src + flow.reshape(2, H * W)
+            if numpy_out:
+                src, dst = src.cpu().numpy(), dst.cpu().numpy()
+                extra['occlusion'] = occlusions.reshape(-1).cpu().numpy()
+                extra['sigma'] = sigma.reshape(-1).cpu().numpy()
+            return src, dst, extra
+        raise ValueError(f'unknown mode {mode}')
+
+
+def downsample_flow_8(flow, mode='bilinear'):
+    """(B, xy, H, W) -> (B, xy, H/8, W/8), values / 8 (raft.py:98-101)."""
+    size = (flow.shape[2] // 8, flow.shape[3] // 8)
+    return F.interpolate(flow, size=size, mode=mode, align_corners=True) / 8

