@@ -88,7 +88,8 @@ int mftb200_sample_points(const float* field, int C, int H, int W, const float* 
 /* ---- diagnostics / test hooks ---------------------------------------------------------------- */
 int mftb200_device_error_flag(mftb200_ctx* ctx);          /* syncs; 0 = clean */
 /* keys: "conv_impl" 0 = tcgen05 (product), 1 = SIMT cross-check kernel (tests only); "iters" = GRU
- * iterations; "profile" 0|1 = per-launch event timing (see mftb200_profile_fetch). */
+ * iterations; "profile" 0|1 = per-launch event timing (see mftb200_profile_fetch); "cluster" (0 = auto,
+ * 1|2|4|8) and "smem_cap_kib" = conv-kernel tuning knobs read by the next mftb200_configure. */
 int mftb200_set_option(mftb200_ctx* ctx, const char* key, int value);
 /* Named internal buffer for stage-level parity tests ("fmap_slots", "net_slots", "corr_l0", ...). */
 int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t* bytes);
@@ -108,6 +109,13 @@ int mftb200_profile_fetch(mftb200_ctx* ctx, double* ms_by_kind /*[2]*/, long lon
 int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
                         float* out_dev, int impl, mftb200_stream stream);
+
+/* Same launch repeated `reps` times with device timing (tuning aid): cluster / smem_cap_kib < 0 keep the
+ * current setting, 0 = automatic; avg_ms receives the mean of launches 2..reps. */
+int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                         float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
+                         mftb200_stream stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ def _declare(lib):
         'mftb200_debug_read': (ci, [vp, C.c_char_p, vp, C.c_size_t]),
         'mftb200_profile_fetch': (ci, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
         'mftb200_launch_count': (C.c_longlong, [vp]),
+        'mftb200_conv2d_bench': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci,
+                                      C.POINTER(C.c_float), vp]),
         'mftb200_conv2d_test': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     }
     for name, (res, args) in sig.items():

@@ -39,6 +39,8 @@ struct ConvGeom {
     int n_tile, n_tiles;          // couts per CTA (multiple of 16, <= 256), CTAs along cout
     int b_rows_per_batch;         // B-matrix row offset per batch entry (correlation), 0 for weights
     int stages, tmem_cols;
+    int cluster;                  // CTAs per cluster sharing (multicasting) the B operand: 1, 2, 4 or 8
+    int total_tiles;              // real tiles per batch entry * nbatch is checked in-kernel via b < nbatch
 };
 
 struct ConvEpi {
@@ -82,6 +84,11 @@ void choose_tile(int H, int W, int* tile_h, int* tile_w);
 const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a_cin, int in_H, int in_W, int batch,
                            int stride, const TapList& taps, const __half* wt, int cout_pad, int n_tile,
                            int b_rows_per_batch, int force_tile_h, int force_tile_w);
+
+// Test / tuning override for the cluster size chosen by conv_plan_init (0 = automatic).
+void conv_set_forced_cluster(int c);
+// Caps the shared memory a CTA may use for pipeline stages (KiB, 0 = default 200).
+void conv_set_smem_cap_kib(int kib);
 
 // Launch on `stream`; nbatch <= batch given at init.  use_simt=1 runs the SIMT cross-check kernel.
 const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt);

@@ -621,6 +621,8 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()
+    if (strcmp(key, "smem_cap_kib") == 0) { conv_set_smem_cap_kib(value); return MFTB200_OK; }      // next configure()
     return c->fail(MFTB200_ERR_ARG, "set_option: unknown key %s", key);
 }
 
@@ -674,10 +676,25 @@ int mftb200_debug_read(mftb200_ctx* c, const char* name, void* dst_device, size_
     return MFTB200_OK;
 }
 
+int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                         float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
+                         mftb200_stream stream);
+
 int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
                         float* out_dev, int impl, mftb200_stream stream) {
-    if (!x_dev || !w_dev || !out_dev || kh * kw > kMaxTaps) return MFTB200_ERR_ARG;
+    return mftb200_conv2d_bench(x_dev, B, H, W, pitch, cin, w_dev, bias_dev, cout_pad, n_tile, kh, kw, stride, relu,
+                                out_dev, impl, -1, -1, 1, nullptr, stream);
+}
+
+int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                         float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
+                         mftb200_stream stream) {
+    if (!x_dev || !w_dev || !out_dev || kh * kw > kMaxTaps || reps < 1) return MFTB200_ERR_ARG;
+    if (cluster >= 0) conv_set_forced_cluster(cluster);
+    if (smem_cap_kib >= 0) conv_set_smem_cap_kib(smem_cap_kib);
     ConvPlan p;
     const char* e = conv_plan_init(&p, reinterpret_cast<const __half*>(x_dev), pitch, cin, H, W, B, stride,
                                    taps_rect(kh, kw), reinterpret_cast<const __half*>(w_dev), cout_pad, n_tile, 0, 0, 0);
@@ -693,12 +710,25 @@ int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, i
     p.mode = EPI_F32;
     p.e.bias = bias_dev; p.e.scale = 1.0f; p.e.relu = relu; p.e.n_valid = cout_pad;
     p.e.out32 = out_dev; p.e.out32_stride = cout_pad; p.e.out32_coff = 0; p.e.err_flag = flag;
-    e = conv_launch(p, B, static_cast<cudaStream_t>(stream), impl);
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    e = conv_launch(p, B, static_cast<cudaStream_t>(stream), impl);          // warm-up / the tested launch
+    cudaEventRecord(ev0, static_cast<cudaStream_t>(stream));
+    for (int r = 1; r < reps && !e; ++r) e = conv_launch(p, B, static_cast<cudaStream_t>(stream), impl);
+    cudaEventRecord(ev1, static_cast<cudaStream_t>(stream));
     if (e) {
         g_create_error = e;
         return MFTB200_ERR_CUDA;
     }
     cudaError_t ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (ce == cudaSuccess && avg_ms && reps > 1) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        *avg_ms = ms / (reps - 1);
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
     if (ce != cudaSuccess) {
         g_create_error = cudaGetErrorString(ce);
         return MFTB200_ERR_CUDA;

@@ -1,0 +1,246 @@
+"""Host-side logic on CPU: C-ABI surface, weight packing, config semantics, tracker bookkeeping,
+world-size-2 gloo run of the flow-sharding logic.  No GPU, no compute calls into the library."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mft_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from mft_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'mft_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(mftb200_[a-z0-9_]+)\s*\(', header)))
+    assert len(declared) >= 15
+    bound = set(_lib.exported_symbols())                  # dlopen + getattr of every bound symbol
+    nm = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf'\bT {name}\b', nm), f'{name} declared in the header but not exported'
+        assert name in bound, f'{name} exported but not bound in mft_b200/_lib.py'
+    assert _lib.lib().mftb200_version().decode().startswith('mft_b200')
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'mft_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.h', '.cuh')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, re.M), f
+
+
+def _unpack(packed, cout):
+    w16, bias, cout_pad, ktot, bias_len = packed
+    return torch.from_numpy(w16.view(np.float16).astype(np.float32))[:cout], torch.from_numpy(bias)[:cout]
+
+
+def _im2col(x, kh, kw, cin_pad):
+    """x (1,C,H,W) -> (H*W, taps*cin_pad) with K order (tap, channel), zero padded."""
+    _, C, H, W = x.shape
+    xp = F.pad(x, (kw // 2, kw // 2, kh // 2, kh // 2))
+    cols = []
+    for ky in range(kh):
+        for kx in range(kw):
+            patch = xp[0, :, ky:ky + H, kx:kx + W].reshape(C, H * W).t()
+            cols.append(F.pad(patch, (0, cin_pad - C)))
+    return torch.cat(cols, 1)
+
+
+@pytest.mark.parametrize('shape', [(24, 7, 3, 3), (130, 20, 1, 5), (70, 33, 5, 1), (324, 16, 1, 1)])
+def test_pack_layout_matches_conv(shape):
+    from mft_b200 import weights as WT
+    cin, cout, kh, kw = shape
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(cout, cin, kh, kw, generator=g).half().float()
+    b = torch.randn(cout, generator=g)
+    x = torch.randn(1, cin, 6, 9, generator=g)
+    W2, b2 = _unpack(WT._pack(w, b), cout)
+    cin_pad = (cin + 63) // 64 * 64
+    got = _im2col(x, kh, kw, cin_pad) @ W2.t() + b2
+    ref = F.conv2d(x, w, b, padding=(kh // 2, kw // 2))[0].reshape(cout, -1).t()
+    assert (got - ref).abs().max() < 1e-3
+
+
+def test_pack_all_semantics(seeded_weights):
+    """BN folding, z|r stacking, q input permutation, OU stacking / block diagonal, 7x7 im2col order."""
+    from mft_b200 import weights as WT
+    W = seeded_weights
+    P = dict(zip(WT.LAYER_NAMES, WT.pack_all(W)))
+    g = torch.Generator().manual_seed(1)
+    # cnet layer1.0.conv1 + BN folded == oracle conv -> batch_norm_eval
+    x = torch.randn(1, 64, 5, 7, generator=g)
+    ref = O.batch_norm_eval(O._conv(x, W, 'cnet.layer1.0.conv1', padding=1), W, 'cnet.layer1.0.norm1')
+    W2, b2 = _unpack(P['cnet.layer1.0.conv1'], 64)
+    got = (_im2col(x, 3, 3, 64) @ W2.t() + b2).t().reshape(1, 64, 5, 7)
+    assert (got - ref).abs().max() < 5e-3
+    # downsample conv folds norm3
+    ref = O.batch_norm_eval(O._conv(x, W, 'cnet.layer2.0.downsample.0'), W, 'cnet.layer2.0.norm3')
+    W2, b2 = _unpack(P['cnet.layer2.0.downsample.0'], 96)
+    assert ((_im2col(x, 1, 1, 64) @ W2.t() + b2).t().reshape(1, 96, 5, 7) - ref).abs().max() < 5e-3
+    # GRU: z|r stacked; q consumes [inp | motion | r*h]
+    h, inp, mot, rh = (torch.randn(1, 128, 4, 6, generator=g) for _ in range(4))
+    hx = torch.cat([h, inp, mot], 1)
+    W2, b2 = _unpack(P['gru_zr1'], 256)
+    got = (_im2col(hx, 1, 5, 384) @ W2.t() + b2).t().reshape(1, 256, 4, 6)
+    assert (got[:, :128] - O._conv(hx, W, 'update_block.gru.convz1', padding=(0, 2))).abs().max() < 5e-3
+    assert (got[:, 128:] - O._conv(hx, W, 'update_block.gru.convr1', padding=(0, 2))).abs().max() < 5e-3
+    W2, b2 = _unpack(P['gru_q2'], 128)
+    got = (_im2col(torch.cat([inp, mot, rh], 1), 5, 1, 384) @ W2.t() + b2).t().reshape(1, 128, 4, 6)
+    ref = O._conv(torch.cat([rh, inp, mot], 1), W, 'update_block.gru.convq2', padding=(2, 0))
+    assert (got - ref).abs().max() < 5e-3
+    # OU heads: conv1 stacked, conv2 block diagonal
+    x712 = torch.randn(1, 712, 4, 6, generator=g)
+    W2, b2 = _unpack(P['ou1'], 256)
+    hid = torch.relu((_im2col(x712, 3, 3, 768) @ W2.t() + b2).t().reshape(1, 256, 4, 6))
+    W3, b3 = _unpack(P['ou2'], 3)
+    got = (_im2col(hid, 3, 3, 256) @ W3.t() + b3).t().reshape(1, 3, 4, 6)
+    occ = O._conv(torch.relu(O._conv(x712, W, 'occlusion_block.occl_head.conv1', padding=1)), W, 'occlusion_block.occl_head.conv2', padding=1)
+    unc = O._conv(torch.relu(O._conv(x712, W, 'occlusion_block.uncertainty_head.conv1', padding=1)), W,
+                  'occlusion_block.uncertainty_head.conv2', padding=1)
+    assert (got[:, :2] - occ).abs().max() < 2e-2 and (got[:, 2:] - unc).abs().max() < 2e-2
+    # 7x7 convs are stored for im2col'ed operands: k = (ky*7+kx)*cin + c
+    flow = torch.randn(1, 2, 9, 9, generator=g)
+    W2, b2 = _unpack(P['convf1'], 128)
+    patch = F.pad(flow, (3, 3, 3, 3))[0, :, 4:11, 2:9].permute(1, 2, 0).reshape(1, 98)      # window around (y=4+3.., x=2+3..)
+    ref = O._conv(flow, W, 'update_block.encoder.convf1', padding=3)[0, :, 4, 2]
+    assert ((F.pad(patch, (0, 30)) @ W2.t() + b2)[0] - ref).abs().max() < 5e-3
+
+
+def test_config_semantics(tmp_path):
+    from mft_b200.config import Config, load_config
+    C = Config()
+    assert not C.timers_enabled and not C.foo.bar.baz          # missing -> falsy empty Config
+    C.deltas = [1, 2]
+    assert C.deltas == [1, 2]
+    p = tmp_path / 'cfg.py'
+    p.write_text('from mft_b200.config import Config\ndef get_config():\n    c = Config(); c.x = 3; return c\n')
+    assert load_config(p).x == 3
+    with pytest.raises(AssertionError):
+        load_config(tmp_path / 'missing.py')
+
+
+class _FakeEngine:
+    def __init__(self):
+        self.encoded = {}
+
+    def encode_frame(self, img, slot):
+        self.encoded[slot] = int(img[0, 0, 0])
+
+
+def _tracker_without_gpu(deltas, direction, start, monkeypatch):
+    """mft_b200.MFT.MFT with the engine calls replaced, to exercise the host bookkeeping only."""
+    import mft_b200.MFT as M
+    from mft_b200.config import Config
+    from mft_b200.results import FlowOUTrackingResult
+    trk = object.__new__(M.MFT)
+    C = Config(); C.deltas = deltas; C.occlusion_threshold = 0.02
+    trk.C, trk.device = C, 'cpu'
+    eng = _FakeEngine()
+    trk.flower = type('F', (), {'ensure_geometry': lambda self, H, W: eng})()
+    calls = []
+
+    def fake_refine(lefts, rights, out=None):
+        calls.append((list(lefts), list(rights)))
+        t = out if out is not None else torch.zeros((len(lefts), 4, 8, 8))
+        t.zero_()
+        return t
+    eng.refine = fake_refine
+    monkeypatch.setattr(M, 'chain_select', lambda lefts, right, thr, want_index=False: (torch.zeros((4, 8, 8)), None))
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda: type('S', (), {'synchronize': lambda self: None})())
+    return trk, eng, calls
+
+
+@pytest.mark.parametrize('direction', [1, -1])
+def test_tracker_bookkeeping(direction, monkeypatch):
+    """Live chains, dedup, memory eviction and feature-slot accounting over 80 frames
+    (MFT.py:74-91,157-185) against the oracle's bookkeeping."""
+    deltas = [np.inf, 1, 2, 4, 8, 16, 32]
+    start = 100
+    trk, eng, calls = _tracker_without_gpu(deltas, direction, start, monkeypatch)
+    img = lambda i: np.full((8, 8, 3), i % 251, np.uint8)
+    trk.init(img(start), start_frame_i=start, time_direction=direction)
+    for n in range(1, 80):
+        t = start + n * direction
+        meta = trk.track(img(t))
+        want = O.live_chains(deltas, t, start, direction)
+        assert trk.live_chains() == want
+        lefts, rights = calls[-1]
+        assert len(lefts) == len(want) and len(set(rights)) == 1
+        # every pair's slots hold the frames they should
+        assert [eng.encoded[s] for s in lefts] == [left % 251 for _, left in want]
+        assert eng.encoded[rights[0]] == t % 251
+        keep = {start} | {f for f in range(min(start, t), max(start, t) + 1) if abs(t - f) < 32}
+        assert set(trk.memory) == keep
+        slots = [m['slot'] for m in trk.memory.values()]
+        assert len(set(slots)) == len(slots) and not (set(slots) & set(trk._free_slots))
+        assert tuple(meta.result.flow.shape) == (2, 8, 8)
+    assert [len(c[0]) for c in calls[:5]] == [1, 2, 3, 3, 4] and len(calls[40][0]) == 7
+
+
+def test_results_cpu_paths_match_oracle():
+    from mft_b200.results import FlowOUTrackingResult
+    rng = np.random.default_rng(0)
+    H, W = 20, 30
+    l = np.concatenate([rng.standard_normal((2, H, W)) * 3, rng.uniform(0, 1, (2, H, W))]).astype(np.float32)
+    r = np.concatenate([rng.standard_normal((2, H, W)) * 3, rng.uniform(0, 1, (2, H, W))]).astype(np.float32)
+    res = FlowOUTrackingResult.from_packed(torch.from_numpy(l.copy()))
+    wf, _, _ = O.chain((l[:2], l[2:3], l[3:4]), (r[:2], r[2:3], r[3:4]))
+    assert np.abs(res.chain(torch.from_numpy(r[:2])).numpy() - wf).max() < 1e-4
+    assert res.packed().data_ptr() == res.flow.data_ptr()            # views, no copy
+    c = res.clone(); c.occlusion[:] = 1
+    assert float(res.occlusion.max()) < 1
+    ident = FlowOUTrackingResult.identity((H, W))
+    assert float(ident.packed().abs().max()) == 0 and not ident.invalid_mask().any()
+    pts = torch.tensor([[0.0, 0.0], [W - 1.0, H - 1.0], [3.5, 4.25]])
+    assert torch.allclose(ident.warp_forward_points(pts), pts)
+    img = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    assert np.abs(ident.warp_forward(img) - img).max() < 1e-6         # zero flow splats in place
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from mft_b200.dist import FlowShardedTracker
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    out.put((rank, _run_sharded(world)))
+    dist.destroy_process_group()
+
+
+def _run_sharded(world):
+    from mft_b200.dist import FlowShardedTracker
+    H, W, T = 6, 8, 11
+    deltas = [np.inf, 1, 2, 4]
+
+    def flow_fn(t, live):        # deterministic stand-in for encode + refine
+        return torch.stack([torch.full((4, H, W), float(t * 10 + (0 if np.isinf(d) else d))) for d, _ in live])
+
+    def select_fn(lefts, right):  # deterministic stand-in for chain_select
+        return sum(l * 0.5 for l in lefts) / len(lefts) + right.mean(0)
+    trk = FlowShardedTracker(deltas, T, (H, W), flow_fn, select_fn, 'cpu')
+    res = trk.run()
+    return {k: float(v.sum()) for k, v in res.items()}
+
+
+def test_flow_sharding_world2_gloo_matches_single_process():
+    import torch.multiprocessing as mp
+    want = _run_sharded(1)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == want and got[1] == want
+    from mft_b200.dist import shard_items
+    assert shard_items(10, 1, 4) == [1, 5, 9] and sorted(sum((shard_items(10, r, 4) for r in range(4)), [])) == list(range(10))

@@ -1,0 +1,51 @@
+"""Conv-kernel tuning sweep on the hot layer shapes of the 512x512, 7-pair refinement loop."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mft_b200 import engine as E, weights as WT   # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+
+LAYERS = {   # name: (cin, cout, kh, kw, n_tile)
+    'convc1': (324, 256, 1, 1, 256), 'convc2': (256, 192, 3, 3, 192), 'convf1': (98, 128, 1, 1, 128),
+    'convf2': (128, 64, 3, 3, 64), 'convm': (256, 126, 3, 3, 128), 'gru_zr': (384, 256, 1, 5, 256),
+    'gru_q': (384, 128, 5, 1, 128), 'fh1': (128, 256, 3, 3, 256), 'fh2': (256, 2, 3, 3, 16), 'ou1': (712, 256, 3, 3, 256),
+}
+
+
+def run(name, cluster, smem, B=7, H=64, W=64, reps=20, check=True):
+    cin, cout, kh, kw, n_tile = LAYERS[name]
+    g = torch.Generator().manual_seed(1)
+    pitch = (cin + 7) // 8 * 8
+    x = torch.randn(B, H, W, pitch, generator=g).half().cuda()
+    w = (torch.randn(cout, cin, kh, kw, generator=g) / np.sqrt(cin * kh * kw)).half().float()
+    b = torch.randn(cout, generator=g)
+    w16, bias, cout_pad, ktot, _ = WT._pack(w, b, cout_pad=(cout + n_tile - 1) // n_tile * n_tile)
+    wd = torch.from_numpy(w16.view(np.float16)).cuda()
+    bd = torch.from_numpy(bias).cuda()
+    try:
+        out, ms = E.conv2d_bench(x, wd, bd, cin, cout_pad, n_tile, kh, kw, 1, False, cluster, smem, reps)
+    except Exception as ex:
+        return f'{name:7s} cluster={cluster} smem={smem}: EXC {ex}'
+    err = -1.0
+    if check:
+        ref = torch.nn.functional.conv2d(x[..., :cin].float().permute(0, 3, 1, 2), w.cuda(), b.cuda(),
+                                         padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1)
+        err = (out[..., :cout] - ref).abs().max().item()
+    flops = 2.0 * B * H * W * cin * kh * kw * cout
+    return f'{name:7s} cluster={cluster} smem={smem:3d}: {ms * 1e3:7.1f} us  {flops / ms / 1e9:7.1f} TFLOP/s  maxerr={err:.2e}'
+
+
+if __name__ == '__main__':
+    names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(LAYERS)
+    clusters = [int(c) for c in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['1', '2', '4', '8'])]
+    smems = [int(c) for c in (sys.argv[3].split(',') if len(sys.argv) > 3 else ['200'])]
+    for n in names:
+        for c in clusters:
+            for s in smems:
+                print(run(n, c, s), flush=True)
