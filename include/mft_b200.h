@@ -117,6 +117,14 @@ int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, 
                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
                          mftb200_stream stream);
 
+/* As above; timing_dev (device int64 [n_ctas][16], may be NULL) receives per-CTA phase timestamps of the LAST
+ * launch: clock64 at entry, set-up done, first stage landed, MMAs issued, accumulator ready, epilogue done,
+ * exit; [7] = globaltimer ns at entry. */
+int mftb200_conv2d_bench2(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                          const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
+                          long long* timing_dev, mftb200_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,8 @@ def _declare(lib):
         'mftb200_launch_count': (C.c_longlong, [vp]),
         'mftb200_conv2d_bench': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci,
                                       C.POINTER(C.c_float), vp]),
+        'mftb200_conv2d_bench2': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci,
+                                       C.POINTER(C.c_float), vp, vp]),
         'mftb200_conv2d_test': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     }
     for name, (res, args) in sig.items():

@@ -31,11 +31,12 @@ constexpr int kChunkK = 64;       // fp16 channels per pipeline stage (= one 128
 struct ConvGeom {
     int H, W;                     // OUTPUT height / width
     int nbatch;                   // batch entries covered by this launch
-    int tile_h, tile_w;           // tile_h * tile_w == 128
+    int tile_h, tile_w;           // tile_h * tile_w == 128, tile_w a power of two
+    int tile_w_log2;
     int tiles_x, tiles_y;
     int stride;                   // input step per output pixel (1 or 2)
     int ntaps, kchunks;           // K loop = ntaps * kchunks stages of 64 channels
-    int8_t dy[kMaxTaps + 3], dx[kMaxTaps + 3];
+    int kh, kw;                   // taps form a centred kh x kw window, row-major: tap = ky*kw + kx
     int n_tile, n_tiles;          // couts per CTA (multiple of 16, <= 256), CTAs along cout
     int b_rows_per_batch;         // B-matrix row offset per batch entry (correlation), 0 for weights
     int stages, tmem_cols;
@@ -56,6 +57,7 @@ struct ConvEpi {
     float* coords1;               // [pixel][2]
     float* delta32;               // [pixel][2]
     int* err_flag;
+    long long* timing;            // optional per-CTA phase timestamps [cta][8] (tuning aid), nullptr in product runs
 };
 
 // Fully described launch (built once per layer at configure time).
@@ -70,8 +72,7 @@ struct ConvPlan {
 };
 
 struct TapList {
-    int n;
-    int8_t dy[kMaxTaps], dx[kMaxTaps];
+    int n, kh, kw;
 };
 TapList taps_rect(int kh, int kw);    // kh x kw window centred (odd sizes), row-major (ky, kx)
 

@@ -19,104 +19,111 @@ namespace mftb {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// The epilogue handles 4 consecutive output columns of one pixel per call.  The tensor-core kernel stages the
+// accumulator tile through shared memory so that the 8 lanes sharing a pixel row touch 8 consecutive 16-byte
+// (fp32) / 8-byte (fp16) segments: every global load and store of the epilogue is coalesced.  Global INPUTS of
+// the epilogue (residual, GRU state) are fetched by epi_prefetch for several pixels before any is consumed, so
+// their L2 latencies overlap.
+struct EpiAux {
+    float4 a, b;
+};
+
 template <int MODE>
-__device__ __forceinline__ void epilogue32(const ConvEpi& e, float (&v)[32], int col0, long pix) {
-    if (col0 >= e.n_valid) return;
-    if (e.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + col0 + j);
-    }
+__device__ __forceinline__ EpiAux epi_prefetch(const ConvEpi& e, int col, long pix) {
+    EpiAux x;
+    x.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    x.b = x.a;
+    if (col >= e.n_valid) return x;
     if constexpr (MODE == EPI_F16) {
-        if (e.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (e.res16 != nullptr) {
-            const __half* r = e.res16 + pix * e.res_stride + e.res_coff + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (col0 + j < e.n_valid) v[j] = fmaxf(v[j] + __half2float(r[j]), 0.0f);
-        }
-        __half* o = e.out16 + pix * e.out16_stride + e.out16_coff + col0;
-        if (col0 + 32 <= e.n_valid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                __align__(16) __half2 h[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                *reinterpret_cast<uint4*>(o + j) = *reinterpret_cast<const uint4*>(h);
-            }
-        } else {
-            for (int j = 0; j < 32 && col0 + j < e.n_valid; ++j) o[j] = __float2half_rn(v[j]);
-        }
-    } else if constexpr (MODE == EPI_F32) {
-        float* o = e.out32 + pix * e.out32_stride + e.out32_coff + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float x = v[j] * e.scale;
-            if (e.relu) x = fmaxf(x, 0.0f);
-            v[j] = x;
-        }
-        if (col0 + 32 <= e.n_valid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-            for (int j = 0; j < 32 && col0 + j < e.n_valid; ++j) o[j] = v[j];
-        }
-    } else if constexpr (MODE == EPI_CNET) {
-        if (col0 < 128) {
-            float* o = e.out32 + pix * 128 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(tanhf(v[j]), tanhf(v[j + 1]), tanhf(v[j + 2]), tanhf(v[j + 3]));
-        } else {
-            __half* o = e.out16 + pix * 128 + (col0 - 128);
-#pragma unroll
-            for (int j = 0; j < 32; j += 2)
-                *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(fmaxf(v[j], 0.0f), fmaxf(v[j + 1], 0.0f));
+        if (e.res16 != nullptr && col + 4 <= e.n_valid) {
+            const uint2 rr = *reinterpret_cast<const uint2*>(e.res16 + pix * e.res_stride + e.res_coff + col);
+            const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+            const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+            x.a = make_float4(r0.x, r0.y, r1.x, r1.y);
         }
     } else if constexpr (MODE == EPI_GRU_ZR) {
-        if (col0 < 128) {
-            float* o = e.z32 + pix * 128 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) =
-                    make_float4(sigmoidf_(v[j]), sigmoidf_(v[j + 1]), sigmoidf_(v[j + 2]), sigmoidf_(v[j + 3]));
+        if (col >= 128) x.a = *reinterpret_cast<const float4*>(e.h32 + pix * 128 + (col - 128));
+    } else if constexpr (MODE == EPI_GRU_Q) {
+        x.a = *reinterpret_cast<const float4*>(e.h32 + pix * 128 + col);
+        x.b = *reinterpret_cast<const float4*>(e.z32 + pix * 128 + col);
+    } else if constexpr (MODE == EPI_FLOW) {
+        if (col == 0) {
+            const float2 c = *reinterpret_cast<const float2*>(e.coords1 + pix * 2);
+            x.a.x = c.x;
+            x.a.y = c.y;
+        }
+    }
+    return x;
+}
+
+__device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
+    const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    return pk;
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const float4 bb, const EpiAux& ax, int col, long pix) {
+    if (col >= e.n_valid) return;
+    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+    const bool full = col + 4 <= e.n_valid;
+    if constexpr (MODE == EPI_F16) {
+        if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        __half* o = e.out16 + pix * e.out16_stride + e.out16_coff + col;
+        if (full) {
+            if (e.res16 != nullptr) {
+                v.x = fmaxf(v.x + ax.a.x, 0.f); v.y = fmaxf(v.y + ax.a.y, 0.f);
+                v.z = fmaxf(v.z + ax.a.z, 0.f); v.w = fmaxf(v.w + ax.a.w, 0.f);
+            }
+            *reinterpret_cast<uint2*>(o) = pack_half4(v.x, v.y, v.z, v.w);
         } else {
-            const float* h = e.h32 + pix * 128 + (col0 - 128);
-            __half* o = e.out16 + pix * e.out16_stride + e.out16_coff + (col0 - 128);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 hv = *reinterpret_cast<const float4*>(h + j);
-                *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(sigmoidf_(v[j]) * hv.x, sigmoidf_(v[j + 1]) * hv.y);
-                *reinterpret_cast<__half2*>(o + j + 2) =
-                    __floats2half2_rn(sigmoidf_(v[j + 2]) * hv.z, sigmoidf_(v[j + 3]) * hv.w);
+            const float a[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4 && col + j < e.n_valid; ++j) {
+                float x = a[j];
+                if (e.res16 != nullptr) x = fmaxf(x + __half2float(e.res16[pix * e.res_stride + e.res_coff + col + j]), 0.f);
+                o[j] = __float2half_rn(x);
             }
         }
-    } else if constexpr (MODE == EPI_GRU_Q) {
-        float* h = e.h32 + pix * 128 + col0;
-        const float* z = e.z32 + pix * 128 + col0;
-        __half* o = e.out16 + pix * e.out16_stride + e.out16_coff + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 hv = *reinterpret_cast<const float4*>(h + j);
-            const float4 zv = *reinterpret_cast<const float4*>(z + j);
-            float4 n;
-            n.x = (1.0f - zv.x) * hv.x + zv.x * tanhf(v[j]);
-            n.y = (1.0f - zv.y) * hv.y + zv.y * tanhf(v[j + 1]);
-            n.z = (1.0f - zv.z) * hv.z + zv.z * tanhf(v[j + 2]);
-            n.w = (1.0f - zv.w) * hv.w + zv.w * tanhf(v[j + 3]);
-            *reinterpret_cast<float4*>(h + j) = n;
-            *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(n.x, n.y);
-            *reinterpret_cast<__half2*>(o + j + 2) = __floats2half2_rn(n.z, n.w);
+    } else if constexpr (MODE == EPI_F32) {
+        v.x *= e.scale; v.y *= e.scale; v.z *= e.scale; v.w *= e.scale;
+        if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        float* o = e.out32 + pix * e.out32_stride + e.out32_coff + col;
+        if (full && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            *reinterpret_cast<float4*>(o) = v;
+        } else {
+            const float a[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4 && col + j < e.n_valid; ++j) o[j] = a[j];
         }
+    } else if constexpr (MODE == EPI_CNET) {
+        if (col < 128) {
+            *reinterpret_cast<float4*>(e.out32 + pix * 128 + col) = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+        } else {
+            *reinterpret_cast<uint2*>(e.out16 + pix * 128 + (col - 128)) =
+                pack_half4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        }
+    } else if constexpr (MODE == EPI_GRU_ZR) {
+        if (col < 128) {
+            *reinterpret_cast<float4*>(e.z32 + pix * 128 + col) =
+                make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+        } else {
+            *reinterpret_cast<uint2*>(e.out16 + pix * e.out16_stride + e.out16_coff + (col - 128)) =
+                pack_half4(sigmoidf_(v.x) * ax.a.x, sigmoidf_(v.y) * ax.a.y, sigmoidf_(v.z) * ax.a.z, sigmoidf_(v.w) * ax.a.w);
+        }
+    } else if constexpr (MODE == EPI_GRU_Q) {
+        const float4 hv = ax.a, zv = ax.b;
+        float4 n;
+        n.x = (1.0f - zv.x) * hv.x + zv.x * tanhf(v.x);
+        n.y = (1.0f - zv.y) * hv.y + zv.y * tanhf(v.y);
+        n.z = (1.0f - zv.z) * hv.z + zv.z * tanhf(v.z);
+        n.w = (1.0f - zv.w) * hv.w + zv.w * tanhf(v.w);
+        *reinterpret_cast<float4*>(e.h32 + pix * 128 + col) = n;
+        *reinterpret_cast<uint2*>(e.out16 + pix * e.out16_stride + e.out16_coff + col) = pack_half4(n.x, n.y, n.z, n.w);
     } else if constexpr (MODE == EPI_FLOW) {
-        if (col0 == 0) {
-            float2 c = *reinterpret_cast<float2*>(e.coords1 + pix * 2);
-            *reinterpret_cast<float2*>(e.delta32 + pix * 2) = make_float2(v[0], v[1]);
-            c.x += v[0];
-            c.y += v[1];
-            *reinterpret_cast<float2*>(e.coords1 + pix * 2) = c;
+        if (col == 0) {
+            *reinterpret_cast<float2*>(e.delta32 + pix * 2) = make_float2(v.x, v.y);
+            *reinterpret_cast<float2*>(e.coords1 + pix * 2) = make_float2(ax.a.x + v.x, ax.a.y + v.y);
         }
     }
 }
@@ -135,13 +142,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_bytes = kTileM * 128;
     const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(g.stages) * stage_bytes);
+    size_t pipe_bytes = static_cast<size_t>(g.stages) * stage_bytes;
+    if (pipe_bytes < 32 * 1024) pipe_bytes = 32 * 1024;            // room for the epilogue staging area
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
     uint64_t* empty = full + g.stages;
     uint64_t* accum_ready = empty + g.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
+    float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 256);   // [4 epilogue warps][256]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long* tstamp = e.timing ? e.timing + (static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+    if (tstamp && threadIdx.x == 0) {
+        tstamp[0] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        tstamp[7] = static_cast<long long>(gt);
+    }
 
     int t = blockIdx.x;
     const int tx = t % g.tiles_x;
@@ -168,6 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (g.cluster > 1) cluster_sync_all(); else __syncthreads();   // barriers visible cluster-wide before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tstamp && threadIdx.x == 0) tstamp[1] = clock64();
     const int T = g.ntaps * g.kchunks;
     const uint32_t crank = g.cluster > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = static_cast<uint16_t>((1u << g.cluster) - 1u);
@@ -178,14 +196,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int x0 = g.stride * tx * g.tile_w;
             const int y0 = g.stride * ty * g.tile_h;
             const int brow = b * g.b_rows_per_batch + ny * g.n_tile;
-            int tap = 0, kc = 0;
+            int kc = 0, kx = 0, ky = 0;
+            const int rx = g.kw / 2, ry = g.kh / 2;
             for (int it = 0; it < T; ++it) {
                 const int s = it % g.stages;
                 const uint32_t ph = (it / g.stages) & 1;
                 if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
                 uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
-                tma_load_4d(sa, &tmA, &full[s], kc * kChunkK, x0 + g.dx[tap], y0 + g.dy[tap], b);
+                tma_load_4d(sa, &tmA, &full[s], kc * kChunkK, x0 + kx - rx, y0 + ky - ry, b);
                 if (g.cluster > 1) {
                     // each CTA fetches 1/cluster of the B slab and multicasts it to all CTAs of the cluster
                     const int slice = g.n_tile / g.cluster;
@@ -194,7 +213,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     tma_load_2d(sa + a_bytes, &tmB, &full[s], it * kChunkK, brow);
                 }
-                if (++kc == g.kchunks) { kc = 0; ++tap; }
+                if (++kc == g.kchunks) {
+                    kc = 0;
+                    if (++kx == g.kw) { kx = 0; ++ky; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -204,6 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = it % g.stages;
                 const uint32_t ph = (it / g.stages) & 1;
                 if (!mbar_wait(&full[s], ph)) { ok = false; break; }
+                if (tstamp && it == 0) tstamp[2] = clock64();
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
@@ -214,37 +237,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // slot reusable once these MMAs have read it (in every CTA that multicasts into it)
                 if (g.cluster > 1) umma_commit_mc(&empty[s], cmask); else umma_commit(&empty[s]);
             }
+            if (tstamp) tstamp[3] = clock64();
             umma_commit(accum_ready);     // accumulator complete
         }
     } else {
         const int q = warp & 3;           // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const int yy = row / g.tile_w, xx = row - yy * g.tile_w;
-        const int y = ty * g.tile_h + yy, x = tx * g.tile_w + xx;
-        const bool valid = (y < g.H) && (x < g.W) && (b < g.nbatch);
-        const long pix = (static_cast<long>(b) * g.H + y) * g.W + x;
+        // bias of this CTA's couts -> this warp's smem copy, while the main loop runs
+        float* bw = bias_s + q * 256;
+        for (int i = lane; i < 256; i += 32)
+            bw[i] = (e.bias != nullptr && i < ((g.n_tile + 31) & ~31)) ? __ldg(e.bias + ny * g.n_tile + i) : 0.0f;
+        __syncwarp();
         ok = mbar_wait(accum_ready, 0);
+        if (tstamp && warp == 2 && lane == 0) tstamp[4] = clock64();
         tc_fence_after();
         if (ok) {
+            // The pipeline slots are idle now (every TMA landed and every MMA read it): reuse them as the
+            // per-warp staging area, 2 x [32 rows][32 fp32] with the 16-byte chunks XOR-swizzled by row.
+            float* stg = reinterpret_cast<float*>(smem) + q * 2048;
+            const int sub = lane >> 3, cq = lane & 7;
+            const int tw_mask = g.tile_w - 1;
             const int nchunk = (g.n_tile + 31) / 32;
             for (int c = 0; c < nchunk; ++c) {
                 uint32_t r[32];
+                const bool tt = tstamp && warp == 2 && lane == 0 && c < 2;
+                if (tt) tstamp[8 + c * 4] = clock64();
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
                 tmem_ld_wait();
-                if (valid) {
-                    float v[32];
+                if (tt) tstamp[9 + c * 4] = clock64();
+                float* buf = stg + (c & 1) * 1024;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epilogue32<MODE>(e, v, ny * g.n_tile + c * 32, pix);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                if (tt) tstamp[10 + c * 4] = clock64();
+                const int col = ny * g.n_tile + c * 32 + cq * 4;
+                const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[4];
+                    long pix[4];
+                    bool val[4];
+                    EpiAux ax[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = (half * 4 + k) * 4 + sub;
+                        v[k] = *reinterpret_cast<const float4*>(buf + rr * 32 + ((cq ^ (rr & 7)) << 2));
+                        const int row = q * 32 + rr;
+                        const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & tw_mask);
+                        val[k] = y < g.H && x < g.W && b < g.nbatch;
+                        pix[k] = (static_cast<long>(b) * g.H + y) * g.W + x;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (val[k]) ax[k] = epi_prefetch<MODE>(e, col, pix[k]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k]);
                 }
+                if (tt) tstamp[11 + c * 4] = clock64();
             }
         }
     }
+    if (tstamp && warp == 2 && lane == 0) tstamp[5] = clock64();
     if (!ok && e.err_flag != nullptr) atomicExch(e.err_flag, 1 + warp);
     tc_fence_before();
     // no CTA may exit while a peer can still multicast into its smem / arrive on its barriers
     if (g.cluster > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
+    if (tstamp && threadIdx.x == 0) tstamp[6] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -270,7 +331,7 @@ conv_simt_kernel(const __half* __restrict__ A, int a_pitch, int a_cin, int in_H,
         float acc[32];
         for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
         for (int tap = 0; tap < g.ntaps; ++tap) {
-            const int iy = g.stride * y + g.dy[tap], ix = g.stride * x + g.dx[tap];
+            const int iy = g.stride * y + tap / g.kw - g.kh / 2, ix = g.stride * x + tap % g.kw - g.kw / 2;
             if (iy < 0 || iy >= in_H || ix < 0 || ix >= in_W) continue;
             const __half* arow = A + ((static_cast<long>(b) * in_H + iy) * in_W + ix) * a_pitch;
             const int kmax = min(a_cin, g.kchunks * kChunkK);
@@ -281,7 +342,13 @@ conv_simt_kernel(const __half* __restrict__ A, int a_pitch, int a_cin, int in_H,
                     if (c0 + j < g.n_tile) acc[j] = fmaf(a, __half2float(Bw[(brow0 + c0 + j) * static_cast<long>(ktot) + kk]), acc[j]);
             }
         }
-        epilogue32<MODE>(e, acc, ny * g.n_tile + c0, pix);
+        for (int j = 0; j < 32; j += 4) {
+            const int col = ny * g.n_tile + c0 + j;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias != nullptr && col < e.n_valid) bb = *reinterpret_cast<const float4*>(e.bias + col);
+            const EpiAux ax = epi_prefetch<MODE>(e, col, pix);
+            epilogue4<MODE>(e, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), bb, ax, col, pix);
+        }
     }
 }
 
@@ -290,13 +357,9 @@ conv_simt_kernel(const __half* __restrict__ A, int a_pitch, int a_cin, int in_H,
 // ------------------------------------------------------------------------------------------
 TapList taps_rect(int kh, int kw) {
     TapList t{};
-    t.n = 0;
-    for (int ky = 0; ky < kh; ++ky)
-        for (int kx = 0; kx < kw; ++kx) {
-            t.dy[t.n] = static_cast<int8_t>(ky - kh / 2);
-            t.dx[t.n] = static_cast<int8_t>(kx - kw / 2);
-            ++t.n;
-        }
+    t.n = kh * kw;
+    t.kh = kh;
+    t.kw = kw;
     return t;
 }
 
@@ -370,15 +433,16 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
         choose_tile(g.H, g.W, &g.tile_h, &g.tile_w);
     }
     if (g.tile_h * g.tile_w != kTileM) return "conv_plan_init: tile must cover 128 pixels";
+    g.tile_w_log2 = 0;
+    while ((1 << g.tile_w_log2) < g.tile_w) ++g.tile_w_log2;
+    if ((1 << g.tile_w_log2) != g.tile_w) return "conv_plan_init: tile width must be a power of two";
     g.tiles_x = (g.W + g.tile_w - 1) / g.tile_w;
     g.tiles_y = (g.H + g.tile_h - 1) / g.tile_h;
     g.stride = stride;
     g.ntaps = taps.n;
     g.kchunks = (a_cin + kChunkK - 1) / kChunkK;
-    for (int i = 0; i < taps.n; ++i) {
-        g.dy[i] = taps.dy[i];
-        g.dx[i] = taps.dx[i];
-    }
+    g.kh = taps.kh;
+    g.kw = taps.kw;
     g.n_tile = n_tile;
     g.n_tiles = (cout_pad + n_tile - 1) / n_tile;
     g.b_rows_per_batch = b_rows_per_batch;
@@ -434,7 +498,9 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
         conv_simt_kernel<MODE><<<grid, 128, 0, stream>>>(p.a_base, p.a_pitch, p.a_cin, p.in_H, p.in_W, p.b_base,
                                                          p.ktot, g, p.e);
     } else {
-        const size_t smem = static_cast<size_t>(g.stages) * (kTileM * 128 + g.n_tile * 128) + (2 * g.stages + 1) * 8 + 16 + 1024;
+        size_t pipe = static_cast<size_t>(g.stages) * (kTileM * 128 + g.n_tile * 128);
+        if (pipe < 32 * 1024) pipe = 32 * 1024;                    // the epilogue stages 4 warps x 2 x 4 KiB in the idle pipeline slots
+        const size_t smem = pipe + 256 /* barriers + TMEM slot */ + 4 * 256 * sizeof(float) /* bias copies */ + 1024;
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

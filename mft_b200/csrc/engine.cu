@@ -680,6 +680,10 @@ int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, 
                          const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
                          mftb200_stream stream);
+int mftb200_conv2d_bench2(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                          const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
+                          long long* timing_dev, mftb200_stream stream);
 
 int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
@@ -692,6 +696,14 @@ int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, 
                          const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
                          mftb200_stream stream) {
+    return mftb200_conv2d_bench2(x_dev, B, H, W, pitch, cin, w_dev, bias_dev, cout_pad, n_tile, kh, kw, stride, relu,
+                                 out_dev, impl, cluster, smem_cap_kib, reps, avg_ms, nullptr, stream);
+}
+
+int mftb200_conv2d_bench2(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
+                          const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
+                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
+                          long long* timing_dev, mftb200_stream stream) {
     if (!x_dev || !w_dev || !out_dev || kh * kw > kMaxTaps || reps < 1) return MFTB200_ERR_ARG;
     if (cluster >= 0) conv_set_forced_cluster(cluster);
     if (smem_cap_kib >= 0) conv_set_smem_cap_kib(smem_cap_kib);
@@ -710,6 +722,7 @@ int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, 
     p.mode = EPI_F32;
     p.e.bias = bias_dev; p.e.scale = 1.0f; p.e.relu = relu; p.e.n_valid = cout_pad;
     p.e.out32 = out_dev; p.e.out32_stride = cout_pad; p.e.out32_coff = 0; p.e.err_flag = flag;
+    p.e.timing = timing_dev;
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);

@@ -120,17 +120,20 @@ def chain_select(lefts, right, occlusion_threshold, want_index=True):
     return out, idx
 
 
-def conv2d_bench(x16, w16, bias, cin, cout_pad, n_tile, kh, kw, stride, relu, cluster, smem_cap_kib, reps):
-    """Tuning aid: the product conv kernel `reps` times; returns (out, mean ms per launch)."""
+def conv2d_bench(x16, w16, bias, cin, cout_pad, n_tile, kh, kw, stride, relu, cluster, smem_cap_kib, reps,
+                 timing=None):
+    """Tuning aid: the product conv kernel `reps` times; returns (out, mean ms per launch).
+    timing: optional CUDA int64 tensor [n_ctas, 8] receiving per-CTA phase timestamps."""
     L = _lib.lib()
     B, H, W, pitch = x16.shape
     Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
     out = torch.zeros((B, Ho, Wo, cout_pad), dtype=torch.float32, device='cuda')
     ms = C.c_float(0)
-    _lib.check(L.mftb200_conv2d_bench(C.c_void_p(x16.data_ptr()), B, H, W, pitch, cin, C.c_void_p(w16.data_ptr()),
-                                      C.c_void_p(bias.data_ptr()), cout_pad, n_tile, kh, kw, stride, int(relu),
-                                      C.c_void_p(out.data_ptr()), 0, int(cluster), int(smem_cap_kib), int(reps),
-                                      C.byref(ms), _stream_ptr()))
+    _lib.check(L.mftb200_conv2d_bench2(C.c_void_p(x16.data_ptr()), B, H, W, pitch, cin, C.c_void_p(w16.data_ptr()),
+                                       C.c_void_p(bias.data_ptr()), cout_pad, n_tile, kh, kw, stride, int(relu),
+                                       C.c_void_p(out.data_ptr()), 0, int(cluster), int(smem_cap_kib), int(reps),
+                                       C.byref(ms), C.c_void_p(timing.data_ptr() if timing is not None else None),
+                                       _stream_ptr()))
     return out, float(ms.value)
 
 

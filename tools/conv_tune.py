@@ -28,17 +28,28 @@ def run(name, cluster, smem, B=7, H=64, W=64, reps=20, check=True):
     w16, bias, cout_pad, ktot, _ = WT._pack(w, b, cout_pad=(cout + n_tile - 1) // n_tile * n_tile)
     wd = torch.from_numpy(w16.view(np.float16)).cuda()
     bd = torch.from_numpy(bias).cuda()
+    timing = torch.zeros((4096, 16), dtype=torch.int64, device='cuda') if os.environ.get('TUNE_TIMING') else None
     try:
-        out, ms = E.conv2d_bench(x, wd, bd, cin, cout_pad, n_tile, kh, kw, 1, False, cluster, smem, reps)
+        out, ms = E.conv2d_bench(x, wd, bd, cin, cout_pad, n_tile, kh, kw, 1, False, cluster, smem, reps, timing)
     except Exception as ex:
         return f'{name:7s} cluster={cluster} smem={smem}: EXC {ex}'
+    extra = ''
+    if timing is not None:
+        t = timing.cpu().numpy()
+        t = t[t[:, 0] != 0].astype(np.float64)
+        d = lambda a, b: (t[:, a] - t[:, b]).mean()
+        span = (t[:, 7].max() - t[:, 7].min()) / 1e3
+        extra = (f'\n        ctas={len(t)} cycles: setup {d(1,0):.0f} fill {d(2,1):.0f} issue {d(3,2):.0f} '
+                 f'accum_ready-after-first {d(4,2):.0f} epilogue {d(5,4):.0f} teardown {d(6,5):.0f} total {d(6,0):.0f}; '
+                 f'CTA start spread {span:.1f} us'
+                 f'\n        chunk0: tmem_ld {d(9,8):.0f} stage {d(10,9):.0f} store {d(11,10):.0f} | chunk1: gap {d(12,11):.0f} tmem_ld {d(13,12):.0f} stage {d(14,13):.0f} store {d(15,14):.0f}')
     err = -1.0
     if check:
         ref = torch.nn.functional.conv2d(x[..., :cin].float().permute(0, 3, 1, 2), w.cuda(), b.cuda(),
                                          padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1)
         err = (out[..., :cout] - ref).abs().max().item()
     flops = 2.0 * B * H * W * cin * kh * kw * cout
-    return f'{name:7s} cluster={cluster} smem={smem:3d}: {ms * 1e3:7.1f} us  {flops / ms / 1e9:7.1f} TFLOP/s  maxerr={err:.2e}'
+    return f'{name:7s} cluster={cluster} smem={smem:3d}: {ms * 1e3:7.1f} us  {flops / ms / 1e9:7.1f} TFLOP/s  maxerr={err:.2e}' + extra
 
 
 if __name__ == '__main__':
