@@ -102,6 +102,8 @@ long long mftb200_launch_count(const mftb200_ctx* ctx);
  * clear) the accumulated device time: index 0 = tensor-core conv/GEMM launches, 1 = the
  * bandwidth-bound kernels.  Used by bench.py for the live roofline numbers. */
 int mftb200_profile_fetch(mftb200_ctx* ctx, double* ms_by_kind /*[2]*/, long long* steps_by_kind /*[2]*/);
+/* Per-step event times in launch order (does not clear; call before mftb200_profile_fetch). */
+int mftb200_profile_steps(mftb200_ctx* ctx, float* ms, int* kinds, int max_steps, int* n_steps);
 
 /* Stand-alone convolution through the product kernel, for unit tests: x fp16 NHWC
  * (B,H,W,pitch) view of `cin` channels, packed weights as in upload_layer, taps = kh x kw

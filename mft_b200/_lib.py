@@ -37,6 +37,7 @@ def _declare(lib):
         'mftb200_debug_buffer': (ci, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         'mftb200_debug_read': (ci, [vp, C.c_char_p, vp, C.c_size_t]),
         'mftb200_profile_fetch': (ci, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+        'mftb200_profile_steps': (ci, [vp, C.POINTER(C.c_float), C.POINTER(ci), ci, C.POINTER(ci)]),
         'mftb200_launch_count': (C.c_longlong, [vp]),
         'mftb200_conv2d_bench': (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci,
                                       C.POINTER(C.c_float), vp]),

@@ -88,6 +88,8 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
 
 // Test / tuning override for the cluster size chosen by conv_plan_init (0 = automatic).
 void conv_set_forced_cluster(int c);
+// Programmatic dependent launch on/off (default on).
+void conv_set_pdl(int on);
 // Caps the shared memory a CTA may use for pipeline stages (KiB, 0 = default 200).
 void conv_set_smem_cap_kib(int kib);
 

@@ -17,7 +17,10 @@ namespace mftb {
 // ------------------------------------------------------------------------------------------
 // fused epilogue on 32 consecutive accumulator columns of one pixel
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// GRU gate non-linearities on the SFU fast path (ex2.approx + rcp.approx, ~2 ulp): absolute error ~1e-7, far
+// below the fp16 rounding of the operands that feed them.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_gate(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 // The epilogue handles 4 consecutive output columns of one pixel per call.  The tensor-core kernel stages the
 // accumulator tile through shared memory so that the 8 lanes sharing a pixel row touch 8 consecutive 16-byte
@@ -114,10 +117,10 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
     } else if constexpr (MODE == EPI_GRU_Q) {
         const float4 hv = ax.a, zv = ax.b;
         float4 n;
-        n.x = (1.0f - zv.x) * hv.x + zv.x * tanhf(v.x);
-        n.y = (1.0f - zv.y) * hv.y + zv.y * tanhf(v.y);
-        n.z = (1.0f - zv.z) * hv.z + zv.z * tanhf(v.z);
-        n.w = (1.0f - zv.w) * hv.w + zv.w * tanhf(v.w);
+        n.x = (1.0f - zv.x) * hv.x + zv.x * tanh_gate(v.x);
+        n.y = (1.0f - zv.y) * hv.y + zv.y * tanh_gate(v.y);
+        n.z = (1.0f - zv.z) * hv.z + zv.z * tanh_gate(v.z);
+        n.w = (1.0f - zv.w) * hv.w + zv.w * tanh_gate(v.w);
         *reinterpret_cast<float4*>(e.h32 + pix * 128 + col) = n;
         *reinterpret_cast<uint2*>(e.out16 + pix * e.out16_stride + e.out16_coff + col) = pack_half4(n.x, n.y, n.z, n.w);
     } else if constexpr (MODE == EPI_FLOW) {
@@ -131,7 +134,7 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
 // ------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;   // warp 0: TMA producer, warp 1: MMA issuer; afterwards ALL 8 warps run the epilogue
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -143,12 +146,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     size_t pipe_bytes = static_cast<size_t>(g.stages) * stage_bytes;
-    if (pipe_bytes < 32 * 1024) pipe_bytes = 32 * 1024;            // room for the epilogue staging area
+    if (pipe_bytes < 64 * 1024) pipe_bytes = 64 * 1024;            // room for the epilogue staging area (8 warps x 8 KiB)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
     uint64_t* empty = full + g.stages;
     uint64_t* accum_ready = empty + g.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
-    float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 256);   // [4 epilogue warps][256]
+    float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 256);   // [8 warps][256]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -185,6 +188,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (g.cluster > 1) cluster_sync_all(); else __syncthreads();   // barriers visible cluster-wide before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail
+    // of the previous kernel in the stream; from here on we touch data it produced.
+    pdl_launch_dependents();
+    pdl_wait();
     if (tstamp && threadIdx.x == 0) tstamp[1] = clock64();
     const int T = g.ntaps * g.kchunks;
     const uint32_t crank = g.cluster > 1 ? cluster_ctarank() : 0u;
@@ -219,6 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
@@ -240,37 +248,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (tstamp) tstamp[3] = clock64();
             umma_commit(accum_ready);     // accumulator complete
         }
-    } else {
-        const int q = warp & 3;           // TMEM lane quarter this warp may access
+        __syncwarp();
+    }
+    {
+        // ---- epilogue: all 8 warps.  Warp w reads TMEM lane quarter w%4 (hardware restriction) and the
+        //      32-column chunks of parity w/4, so each quarter is drained by two warps.
+        const int q = warp & 3;
+        const int cpar = warp >> 2;
         // bias of this CTA's couts -> this warp's smem copy, while the main loop runs
-        float* bw = bias_s + q * 256;
+        float* bw = bias_s + warp * 256;
         for (int i = lane; i < 256; i += 32)
             bw[i] = (e.bias != nullptr && i < ((g.n_tile + 31) & ~31)) ? __ldg(e.bias + ny * g.n_tile + i) : 0.0f;
         __syncwarp();
-        ok = mbar_wait(accum_ready, 0);
+        const bool ok_acc = mbar_wait(accum_ready, 0);
+        ok = ok && ok_acc;
         if (tstamp && warp == 2 && lane == 0) tstamp[4] = clock64();
         tc_fence_after();
-        if (ok) {
+        if (ok_acc) {
             // The pipeline slots are idle now (every TMA landed and every MMA read it): reuse them as the
             // per-warp staging area, 2 x [32 rows][32 fp32] with the 16-byte chunks XOR-swizzled by row.
-            float* stg = reinterpret_cast<float*>(smem) + q * 2048;
+            float* stg = reinterpret_cast<float*>(smem) + warp * 2048;
             const int sub = lane >> 3, cq = lane & 7;
             const int tw_mask = g.tile_w - 1;
             const int nchunk = (g.n_tile + 31) / 32;
-            for (int c = 0; c < nchunk; ++c) {
+            // the 8 pixel rows this lane serves are the same for every column chunk
+            long pixr[8];
+            unsigned valid_bits = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = q * 32 + k * 4 + sub;
+                const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & tw_mask);
+                if (y < g.H && x < g.W && b < g.nbatch) valid_bits |= 1u << k;
+                pixr[k] = (static_cast<long>(b) * g.H + y) * g.W + x;
+            }
+            for (int c = cpar; c < nchunk; c += 2) {
                 uint32_t r[32];
-                const bool tt = tstamp && warp == 2 && lane == 0 && c < 2;
-                if (tt) tstamp[8 + c * 4] = clock64();
+                const bool tt = tstamp && warp == 2 && lane == 0 && c < 4;
+                if (tt) tstamp[8 + (c >> 1) * 4] = clock64();
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
                 tmem_ld_wait();
-                if (tt) tstamp[9 + c * 4] = clock64();
-                float* buf = stg + (c & 1) * 1024;
+                if (tt) tstamp[9 + (c >> 1) * 4] = clock64();
+                float* buf = stg + ((c >> 1) & 1) * 1024;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                         make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
-                if (tt) tstamp[10 + c * 4] = clock64();
+                if (tt) tstamp[10 + (c >> 1) * 4] = clock64();
                 const int col = ny * g.n_tile + c * 32 + cq * 4;
                 const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
 #pragma unroll
@@ -283,10 +307,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < 4; ++k) {
                         const int rr = (half * 4 + k) * 4 + sub;
                         v[k] = *reinterpret_cast<const float4*>(buf + rr * 32 + ((cq ^ (rr & 7)) << 2));
-                        const int row = q * 32 + rr;
-                        const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & tw_mask);
-                        val[k] = y < g.H && x < g.W && b < g.nbatch;
-                        pix[k] = (static_cast<long>(b) * g.H + y) * g.W + x;
+                        val[k] = (valid_bits >> (half * 4 + k)) & 1u;
+                        pix[k] = pixr[half * 4 + k];
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
@@ -295,7 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < 4; ++k)
                         if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k]);
                 }
-                if (tt) tstamp[11 + c * 4] = clock64();
+                if (tt) tstamp[11 + (c >> 1) * 4] = clock64();
             }
         }
     }
@@ -376,6 +398,8 @@ void choose_tile(int H, int W, int* tile_h, int* tile_w) {
     }
 }
 
+static int g_use_pdl = 1;
+void conv_set_pdl(int on) { g_use_pdl = on; }
 static int g_forced_cluster = 0;
 static int g_smem_cap_kib = 0;
 void conv_set_forced_cluster(int c) { g_forced_cluster = c; }
@@ -499,33 +523,38 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
                                                          p.ktot, g, p.e);
     } else {
         size_t pipe = static_cast<size_t>(g.stages) * (kTileM * 128 + g.n_tile * 128);
-        if (pipe < 32 * 1024) pipe = 32 * 1024;                    // the epilogue stages 4 warps x 2 x 4 KiB in the idle pipeline slots
-        const size_t smem = pipe + 256 /* barriers + TMEM slot */ + 4 * 256 * sizeof(float) /* bias copies */ + 1024;
+        if (pipe < 64 * 1024) pipe = 64 * 1024;                    // the epilogue stages 8 warps x 2 x 4 KiB in the idle pipeline slots
+        const size_t smem = pipe + 256 /* barriers + TMEM slot */ + 8 * 256 * sizeof(float) /* bias copies */ + 1024;
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (err != cudaSuccess) return cudaGetErrorString(err);
             attr_set = true;
         }
-        if (g.cluster > 1) {
-            grid.x = (grid.x + g.cluster - 1) / g.cluster * g.cluster;   // phantom CTAs keep the cluster whole
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = grid;
-            cfg.blockDim = dim3(kThreads);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = static_cast<unsigned>(g.cluster);
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            cudaError_t err = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, p.tmA, p.tmB, g, p.e);
-            if (err != cudaSuccess) return cudaGetErrorString(err);
-        } else {
-            conv_tc_kernel<MODE><<<grid, kThreads, smem, stream>>>(p.tmA, p.tmB, g, p.e);
+        if (g.cluster > 1) grid.x = (grid.x + g.cluster - 1) / g.cluster * g.cluster;   // phantom CTAs keep the cluster whole
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (g_use_pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
         }
+        if (g.cluster > 1) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = static_cast<unsigned>(g.cluster);
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, p.tmA, p.tmB, g, p.e);
+        if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     }
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

@@ -621,12 +621,25 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()
     if (strcmp(key, "smem_cap_kib") == 0) { conv_set_smem_cap_kib(value); return MFTB200_OK; }      // next configure()
     return c->fail(MFTB200_ERR_ARG, "set_option: unknown key %s", key);
 }
 
 long long mftb200_launch_count(const mftb200_ctx* c) { return c ? c->launches : 0; }
+
+int mftb200_profile_steps(mftb200_ctx* c, float* ms, int* kinds, int max_steps, int* n_steps) {
+    if (!c || !ms || !kinds || !n_steps) return MFTB200_ERR_ARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return c->fail(MFTB200_ERR_CUDA, "profile_steps: device error");
+    const int n = static_cast<int>(c->prof_kinds.size());
+    *n_steps = n;
+    for (int i = 0; i < n && i < max_steps; ++i) {
+        cudaEventElapsedTime(&ms[i], c->prof_events[2 * i], c->prof_events[2 * i + 1]);
+        kinds[i] = c->prof_kinds[i];
+    }
+    return MFTB200_OK;
+}
 
 int mftb200_profile_fetch(mftb200_ctx* c, double* ms_by_kind, long long* steps_by_kind) {
     if (!c || !ms_by_kind || !steps_by_kind) return MFTB200_ERR_ARG;

@@ -12,13 +12,14 @@ namespace mftb {
 // grid_sample(align_corners=True) round trip (MFT/utils/interpolation.py:63-73 and
 // MFT/RAFT/core/utils/utils.py:98-106); ATen undoes it as ((g+1)/2)*(size-1).
 // ==========================================================================================
+// (x / 2 is written x * 0.5f: bit-identical in IEEE fp32 and avoids the division sequence.)
 __device__ __forceinline__ float roundtrip_mul(float c, float scale, float size_m1) {
     const float g = c * scale - 1.0f;                    // normalize_coords: x*(2/(W-1)) - 1
-    return ((g + 1.0f) / 2.0f) * size_m1;
+    return ((g + 1.0f) * 0.5f) * size_m1;
 }
 __device__ __forceinline__ float roundtrip_div(float c, float size_m1) {
     const float g = (2.0f * c) / size_m1 - 1.0f;         // bilinear_sampler: 2*x/(W-1) - 1
-    return ((g + 1.0f) / 2.0f) * size_m1;
+    return ((g + 1.0f) * 0.5f) * size_m1;
 }
 
 // ==========================================================================================
@@ -351,42 +352,78 @@ void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long row
 // pyramid lookup (core/corr.py:30-51) + flow operands of the motion encoder
 // one warp per (pair, source pixel)
 // ==========================================================================================
+// Per level the 81 sample points of a pixel share one 11x11 integer neighbourhood of its correlation
+// row and only 9 distinct x- and 9 distinct y-coordinates: lanes 0..17 evaluate those 18 coordinates
+// (the oracle's exact round trip), the warp stages the four neighbourhoods in shared memory (484 loads
+// per pixel instead of 4 x 324), then every lane blends its samples from shared memory in the oracle's
+// operation order.
+constexpr int kLkWin = 11;
+
 __global__ void __launch_bounds__(256)
 lookup_kernel(const LookupArgs a) {
+    __shared__ float win[8][4][kLkWin * kLkWin + 3];
+    __shared__ float frac[8][4][18];       // wE for the 9 x samples, wS for the 9 y samples
+    __shared__ int cell[8][4][18];         // window cell of floor(coordinate); kBadCell = non-finite coordinate
+    constexpr int kBadCell = -100000;
     const int npx = a.h * a.w;
-    const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const long pp = static_cast<long>(blockIdx.x) * 8 + wib;
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
     const int lane = threadIdx.x & 31;
     const int n = static_cast<int>(pp % npx);
     const int y = n / a.w, x = n % a.w;
     const float cx = a.coords1[pp * 2], cy = a.coords1[pp * 2 + 1];
     __half* out = a.corr16 + pp * 328;
-    int hl = a.h, wl = a.w;
-    float div = 1.0f;
+
+    {
+        int hl = a.h, wl = a.w;
+        float div = 1.0f;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            // the 18 sample coordinates of this level: lanes 0..8 -> x offsets -4..4, lanes 9..17 -> y offsets
+            const bool isx = lane < 9;
+            const int k = isx ? lane : lane - 9;
+            const float c = (isx ? cx : cy) / div + static_cast<float>(k - 4);
+            const int size = isx ? wl : hl;
+            const float pos = roundtrip_div(c, static_cast<float>(size - 1));
+            const float pf = floorf(pos);
+            const bool fin = isfinite(pos);
+            const int cell_abs = fin ? static_cast<int>(fminf(fmaxf(pf, -32.0f), static_cast<float>(size + 16))) : 0;
+            // window origin = cell of the first sample (lane 0 for x, lane 9 for y)
+            const int X0 = __shfl_sync(0xffffffffu, cell_abs, 0);
+            const int Y0 = __shfl_sync(0xffffffffu, cell_abs, 9);
+            const bool all_fin = __all_sync(0xffffffffu, fin || lane >= 18);
+            if (lane < 18) {
+                frac[wib][l][lane] = pos - pf;
+                cell[wib][l][lane] = all_fin ? cell_abs - (isx ? X0 : Y0) : kBadCell;
+            }
+            const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
+            for (int e = lane; e < kLkWin * kLkWin; e += 32) {
+                const int wy = e / kLkWin, wx = e - wy * kLkWin;
+                const int gx = X0 + wx, gy = Y0 + wy;
+                win[wib][l][e] = (all_fin && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
+                                     ? __ldg(base + static_cast<long>(gy) * wl + gx) : 0.0f;
+            }
+            hl >>= 1; wl >>= 1; div *= 2.0f;
+        }
+    }
+    __syncwarp();
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
-        const float lx = cx / div, ly = cy / div;
-        const float wm1 = static_cast<float>(wl - 1), hm1 = static_cast<float>(hl - 1);
+        const float* W = win[wib][l];
         for (int o = lane; o < 81; o += 32) {
             const int i = o / 9, j = o - i * 9;          // i: x offset index, j: y offset index
-            const float ix = roundtrip_div(lx + static_cast<float>(i - 4), wm1);
-            const float iy = roundtrip_div(ly + static_cast<float>(j - 4), hm1);
+            const int wx = cell[wib][l][i], wy = cell[wib][l][9 + j];
             float r;
-            if (!(isfinite(ix) && isfinite(iy))) {
+            if (wx == kBadCell) {
                 r = NAN;
             } else {
-                const float x0f = floorf(ix), y0f = floorf(iy);
-                const float wE = ix - x0f, wW = 1.0f - wE, wS = iy - y0f, wN = 1.0f - wS;
-                const int x0 = static_cast<int>(fminf(fmaxf(x0f, -2.0f), static_cast<float>(wl + 1)));
-                const int y0 = static_cast<int>(fminf(fmaxf(y0f, -2.0f), static_cast<float>(hl + 1)));
-                const bool xw = x0 >= 0 && x0 < wl, xe = x0 + 1 >= 0 && x0 + 1 < wl;
-                const bool yn = y0 >= 0 && y0 < hl, ys = y0 + 1 >= 0 && y0 + 1 < hl;
-                const long onw = static_cast<long>(y0) * wl + x0;
-                const float vnw = (xw && yn) ? __ldg(base + onw) : 0.0f;
-                const float vne = (xe && yn) ? __ldg(base + onw + 1) : 0.0f;
-                const float vsw = (xw && ys) ? __ldg(base + onw + wl) : 0.0f;
-                const float vse = (xe && ys) ? __ldg(base + onw + wl + 1) : 0.0f;
+                const float wE = frac[wib][l][i], wW = 1.0f - wE, wS = frac[wib][l][9 + j], wN = 1.0f - wS;
+                float vnw = 0.f, vne = 0.f, vsw = 0.f, vse = 0.f;
+                if (wx >= 0 && wx < kLkWin - 1 && wy >= 0 && wy < kLkWin - 1) {
+                    const float* q = W + wy * kLkWin + wx;
+                    vnw = q[0]; vne = q[1]; vsw = q[kLkWin]; vse = q[kLkWin + 1];
+                }
                 r = (wW * wN) * vnw;
                 r = r + (wE * wN) * vne;
                 r = r + (wW * wS) * vsw;
@@ -394,7 +431,6 @@ lookup_kernel(const LookupArgs a) {
             }
             out[l * 81 + o] = __float2half_rn(r);
         }
-        hl >>= 1; wl >>= 1; div *= 2.0f;
     }
     if (lane < 4) out[324 + lane] = __float2half_rn(0.0f);
     // flow = coords1 - coords0 (core/raft.py:179); 7x7x2 zero-padded neighbourhood for convf1

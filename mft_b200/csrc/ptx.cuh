@@ -75,6 +75,12 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm,
         : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: block until every prerequisite grid has completed and its memory is visible.
+// launch_dependents: allow the next grid in the stream to start its prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
