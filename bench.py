@@ -229,11 +229,16 @@ def run_ours(args):
         t += 1
     barrier()
     t0 = time.perf_counter()
+    per_frame = []
     for _ in range(K):
+        t1 = time.perf_counter()
         meta = tracker.track(frames[t])
+        per_frame.append(time.perf_counter() - t1)
         t += 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get('BENCH_DEBUG'):
+        print('e2e per-frame ms:', [round(x * 1e3, 2) for x in per_frame], file=sys.stderr)
     assert tuple(meta.result.flow.shape) == (2, H, W) and not meta.result.flow.is_cuda
     eng.check_device()
     # ---- live per-launch profile of one step (rank 0) ----------------------------------------------

@@ -18,6 +18,30 @@ from .results import FlowOUTrackingResult
 logger = logging.getLogger(__name__)
 
 
+class _PinnedPool:
+    """Recycled pinned host buffers for the per-frame device->host copy of the result.
+
+    cudaHostAlloc / cudaFreeHost cost milliseconds and synchronise the device, so results are handed out as
+    tensors over slots of ONE pinned allocation; a slot returns to the pool when the caller drops the last
+    tensor (or view) that references it.  If the caller keeps more results alive than there are slots (demo.py
+    keeps every frame) the copy falls back to a plain pageable tensor."""
+
+    def __init__(self, shape, slots=6):
+        import weakref
+        self._weakref = weakref
+        self.base = torch.empty((slots,) + tuple(shape), dtype=torch.float32).pin_memory()
+        self.base_np = self.base.numpy()
+        self.free = list(range(slots))
+
+    def take(self):
+        if not self.free:
+            return None
+        i = self.free.pop()
+        view = self.base_np[i]                       # fresh ndarray object; torch.from_numpy keeps it alive
+        self._weakref.finalize(view, self.free.append, i)
+        return torch.from_numpy(view)
+
+
 class MFT:
     def __init__(self, config):
         self.C = config                     # the runner re-assigns tracker.C between runs (run_MFT_tapvid.py:151)
@@ -38,7 +62,9 @@ class MFT:
             raise ValueError(f'deltas up to {TRACKER_SLOTS - 2} are supported (feature-slot budget)')
         self.engine = self.flower.ensure_geometry(self.img_H, self.img_W)
         self._free_slots = list(range(TRACKER_SLOTS))
-        self._host_out = torch.empty((4, self.img_H, self.img_W), dtype=torch.float32).pin_memory()
+        if getattr(self, '_pool_shape', None) != (self.img_H, self.img_W):
+            self._pool = _PinnedPool((4, self.img_H, self.img_W))
+            self._pool_shape = (self.img_H, self.img_W)
         slot = self._free_slots.pop()
         self.engine.encode_frame(img, slot)
         self.memory = {start_frame_i: {'img': img, 'slot': slot,
@@ -121,9 +147,12 @@ class MFT:
         if kwargs.get('device_result', False):
             meta.result = result
         else:
-            self._host_out.copy_(packed, non_blocking=True)
+            host = self._pool.take()                  # pinned slot: asynchronous D2H, one stream sync, no extra copy
+            if host is None:
+                host = torch.empty((4, H, W), dtype=torch.float32)
+            host.copy_(packed, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            meta.result = FlowOUTrackingResult.from_packed(self._host_out.clone())
+            meta.result = FlowOUTrackingResult.from_packed(host)
         if debug:
             meta.selected_delta_i = index
             meta.used_deltas = [d for d, _ in live]

@@ -77,11 +77,16 @@ struct mftb200_ctx {
     struct Step {
         std::function<const char*(mftb200_ctx*, cudaStream_t)> fn;
         int kind = 1;                       // 0 = tensor-core conv / GEMM launch, 1 = bandwidth-bound kernel(s)
+        int lane = 0;                       // 0 = caller's stream, 1 = the engine's side stream (independent branch)
+        int sync = 0;                       // 1 = fork (side stream waits for main), 2 = join (main waits for side)
         Step() = default;
         template <class F>
         Step(F f, int k = 1) : fn(std::move(f)), kind(k) {}
     };
     std::vector<Step> enc_steps, pre_steps, iter_steps, final_steps;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
     std::vector<cudaEvent_t> prof_events;   // pairs
@@ -161,6 +166,12 @@ struct Builder {
     }
 };
 
+mftb200_ctx::Step sync_step(int kind) {
+    mftb200_ctx::Step st;
+    st.sync = kind;
+    return st;
+}
+
 mftb200_ctx::Step conv_step(int plan_idx, bool batched_pairs) {
     return mftb200_ctx::Step([plan_idx, batched_pairs](mftb200_ctx* c, cudaStream_t s) -> const char* {
         c->launches++;
@@ -168,11 +179,10 @@ mftb200_ctx::Step conv_step(int plan_idx, bool batched_pairs) {
     }, 0);
 }
 
-const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
+const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb200_ctx::Step>& S, __half* const* E) {
     const bool inorm = (net == L_FNET);
     const int H2 = c->Hp / 2, W2 = c->Wp / 2, H4 = c->Hp / 4, W4 = c->Wp / 4, H8 = c->h, W8 = c->w;
     const int P2 = H2 * W2;
-    auto& S = c->enc_steps;
     const TapList t1 = taps_rect(1, 1), t3 = taps_rect(3, 3);
 
     // raw -> instance norm (+relu) (+residual) -> out
@@ -190,9 +200,9 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
         Act in{c->patches, 152, 147, 1, P2};
         if (inorm) {
             S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 0, c->raw, 64, 0, 64), false));
-            norm(c->raw, P2, 64, 1, nullptr, c->E[0]);
+            norm(c->raw, P2, 64, 1, nullptr, E[0]);
         } else {
-            S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 1, c->E[0], 64, 0, 64), false));
+            S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 1, E[0], 64, 0, 64), false));
         }
     }
     struct Blk { int c1, c2, ds, cin, cout, stride, Hin, Win; };
@@ -202,10 +212,10 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
         {E_L3_0_C1, E_L3_0_C2, E_L3_0_DS, 96, 128, 2, H4, W4}, {E_L3_1_C1, E_L3_1_C2, -1, 128, 128, 1, H8, W8}};
     int cur = 0;   // index of the buffer holding the block input
     for (const Blk& b : blks) {
-        __half* in = c->E[cur];
-        __half* out = c->E[cur ^ 1];
-        __half* tmp = c->E[2];
-        __half* xd = c->E[3];
+        __half* in = E[cur];
+        __half* out = E[cur ^ 1];
+        __half* tmp = E[2];
+        __half* xd = E[3];
         const int Ho = b.Hin / b.stride, Wo = b.Win / b.stride, Po = Ho * Wo;
         Act ain{in, b.cin, b.cin, b.Hin, b.Win};
         Act atmp{tmp, b.cout, b.cout, Ho, Wo};
@@ -232,7 +242,7 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net) {
     }
     // conv2 (1x1 128 -> 256) into the feature slot
     {
-        Act in{c->E[cur], 128, 128, H8, W8};
+        Act in{E[cur], 128, 128, H8, W8};
         const int mode = inorm ? EPI_F16 : EPI_CNET;
         const int i = B.conv(net + E_CONV2, in, 1, 1, t1, 256, mode);
         if (i >= 0) {
@@ -302,10 +312,15 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     Act a_h{c->X, 512, 128, h, w};
     Act a_fh{c->fhbuf, 256, 256, h, w};
     // motion encoder (update.py:152-160)
+    // the correlation branch (caller's stream) and the flow branch (side stream) are independent until `conv`
+    S.push_back(sync_step(1));
     S.push_back(conv_step(B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
-    S.push_back(conv_step(B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
     S.push_back(conv_step(B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
+    S.back().lane = 1;
+    S.push_back(conv_step(B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
     S.push_back(conv_step(B.conv16(L_CONVF2, a_f1, mp, 1, t3, 64, 1, c->cf, 256, 192, 64), true));
+    S.back().lane = 1;
+    S.push_back(sync_step(2));
     S.push_back(conv_step(B.conv16(L_CONVM, a_cf, mp, 1, t3, 128, 1, c->X, 512, 256, 126), true));
     // SepConvGRU (update.py:108-123): horizontal 1x5 then vertical 5x1
     for (int pass = 0; pass < 2; ++pass) {
@@ -371,8 +386,20 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     return B.err;
 }
 
-int run_steps(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cudaStream_t s) {
+int run_steps(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cudaStream_t main_stream) {
     for (auto& st : steps) {
+        if (c->profile && st.sync != 0) continue;      // profiling serialises everything on the caller's stream
+        if (st.sync == 1) {            // fork: the side stream may start once everything queued so far is done
+            cudaEventRecord(c->ev_fork, main_stream);
+            cudaStreamWaitEvent(c->side, c->ev_fork, 0);
+            continue;
+        }
+        if (st.sync == 2) {            // join
+            cudaEventRecord(c->ev_join, c->side);
+            cudaStreamWaitEvent(main_stream, c->ev_join, 0);
+            continue;
+        }
+        cudaStream_t s = (st.lane && !c->profile) ? c->side : main_stream;
         if (c->profile) {
             cudaEvent_t a, b;
             cudaEventCreate(&a);
@@ -422,6 +449,9 @@ int mftb200_create(mftb200_ctx** out) {
         return MFTB200_ERR_CUDA;
     }
     cudaMemset(c->err_flag, 0, 256);
+    cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     *out = c;
     return MFTB200_OK;
 }
@@ -434,6 +464,9 @@ void mftb200_destroy(mftb200_ctx* c) {
         cudaFree(L.bias);
     }
     cudaFree(c->err_flag);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
 }
 
@@ -480,6 +513,7 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     chk(c->frame_u8 = c->dalloc<uint8_t>(static_cast<size_t>(H) * W * 3));
     chk(c->patches = c->dalloc<__half>(P2 * 152));
     for (int i = 0; i < 4; ++i) chk(c->E[i] = c->dalloc<__half>(P2 * 64));
+    for (int i = 0; i < 4; ++i) chk(c->E2[i] = c->dalloc<__half>(P2 * 64));
     chk(c->raw = c->dalloc<__half>(P2 * 64));
     chk(c->raw2 = c->dalloc<__half>(P2 * 64));
     chk(c->sums = c->dalloc<double>(2 * 256));
@@ -521,8 +555,20 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
         cc->launches++;
         return nullptr;
     });
-    const char* e = build_encoder(c, B, L_FNET);
-    if (!e) e = build_encoder(c, B, L_CNET);
+    // fnet (caller's stream) and cnet (side stream) only share the read-only patch matrix: run them concurrently
+    std::vector<mftb200_ctx::Step> fsteps, csteps;
+    const char* e = build_encoder(c, B, L_FNET, fsteps, c->E);
+    if (!e) e = build_encoder(c, B, L_CNET, csteps, c->E2);
+    if (!e) {
+        for (auto& st : csteps) st.lane = 1;
+        c->enc_steps.push_back(sync_step(1));
+        size_t fi = 0, ci = 0;
+        while (fi < fsteps.size() || ci < csteps.size()) {      // interleaved issue order keeps both streams fed
+            if (fi < fsteps.size()) c->enc_steps.push_back(fsteps[fi++]);
+            if (ci < csteps.size()) c->enc_steps.push_back(csteps[ci++]);
+        }
+        c->enc_steps.push_back(sync_step(2));
+    }
     if (!e) e = build_refine(c, B);
     if (e) {
         std::string msg = e;

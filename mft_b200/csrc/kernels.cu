@@ -7,6 +7,29 @@
 
 namespace mftb {
 
+// Programmatic dependent launch: every kernel of the path is launched with the stream-serialisation attribute,
+// signals its dependents at entry and waits for its prerequisites before touching memory, so launch latency and
+// CTA start-up overlap the tail of the previous kernel.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ==========================================================================================
 // shared bilinear helper: the reference feeds pixel coordinates through a normalise ->
 // grid_sample(align_corners=True) round trip (MFT/utils/interpolation.py:63-73 and
@@ -27,6 +50,7 @@ __device__ __forceinline__ float roundtrip_div(float c, float size_m1) {
 // ==========================================================================================
 __global__ void __launch_bounds__(256)
 chain_select_kernel(const ChainSelectArgs a, const float sx, const float sy) {
+    pdl_enter();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= a.W) return;
@@ -96,7 +120,7 @@ void launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream) {
     const float sx = static_cast<float>(2.0 / (a.W - 1));
     const float sy = static_cast<float>(2.0 / (a.H - 1));
     dim3 grid((a.W + 255) / 256, a.H);
-    chain_select_kernel<<<grid, 256, 0, stream>>>(a, sx, sy);
+    launch_pdl(chain_select_kernel, grid, dim3(256), 0, stream, a, sx, sy);
 }
 
 // ==========================================================================================
@@ -175,6 +199,7 @@ void launch_sample_points(const float* field, int C, int H, int W, const float* 
 __global__ void __launch_bounds__(256)
 frame_patches_kernel(const uint8_t* __restrict__ bgr, int H, int W, int Hp, int Wp, int pl, int pt,
                      __half* __restrict__ patches, long total) {
+    pdl_enter();
     const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int k = static_cast<int>(i % 152);
@@ -197,8 +222,8 @@ frame_patches_kernel(const uint8_t* __restrict__ bgr, int H, int W, int Hp, int 
 void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
                           cudaStream_t stream) {
     const long total = static_cast<long>(Hp / 2) * (Wp / 2) * 152;
-    frame_patches_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(bgr, H, W, Hp, Wp, pad_left,
-                                                                                         pad_top, patches, total);
+    launch_pdl(frame_patches_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, bgr, H, W, Hp,
+               Wp, pad_left, pad_top, patches, total);
 }
 
 // ==========================================================================================
@@ -208,6 +233,7 @@ constexpr int kStatThreads = 192;   // divisible by C/2 for C in {64, 96, 128}
 
 __global__ void __launch_bounds__(kStatThreads)
 instnorm_stats_kernel(const __half* __restrict__ raw, int P, int C, int pix_per_block, double* __restrict__ sums) {
+    pdl_enter();
     __shared__ float red[2][kStatThreads * 2];
     const int b = blockIdx.y;
     const int c2 = C / 2;
@@ -241,12 +267,13 @@ void launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums,
     cudaMemsetAsync(sums, 0, sizeof(double) * B * 2 * C, stream);
     const int pix_per_block = 256;
     dim3 grid((P + pix_per_block - 1) / pix_per_block, B);
-    instnorm_stats_kernel<<<grid, kStatThreads, 0, stream>>>(raw, P, C, pix_per_block, sums);
+    launch_pdl(instnorm_stats_kernel, grid, dim3(kStatThreads), 0, stream, raw, P, C, pix_per_block, sums);
 }
 
 __global__ void __launch_bounds__(256)
 instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict__ sums, int P, int C, int relu,
                       const __half2* __restrict__ res, __half2* __restrict__ out, long total2) {
+    pdl_enter();
     const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total2) return;
     const int c2 = C / 2;
@@ -271,9 +298,9 @@ instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict_
 void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
                            __half* out, cudaStream_t stream) {
     const long total2 = static_cast<long>(B) * P * C / 2;
-    instnorm_apply_kernel<<<static_cast<unsigned>((total2 + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const __half2*>(raw), sums, P, C, relu, reinterpret_cast<const __half2*>(res),
-        reinterpret_cast<__half2*>(out), total2);
+    launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total2 + 255) / 256)), dim3(256), 0, stream,
+               reinterpret_cast<const __half2*>(raw), sums, P, C, relu, reinterpret_cast<const __half2*>(res),
+               reinterpret_cast<__half2*>(out), total2);
 }
 
 // ==========================================================================================
@@ -282,6 +309,7 @@ void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, 
 // ==========================================================================================
 __global__ void __launch_bounds__(128)
 pair_setup_kernel(const PairSetup a) {
+    pdl_enter();
     const int npx = a.h * a.w;
     const long pp = blockIdx.x;                 // pair * npx + n
     const int pair = static_cast<int>(pp / npx), n = static_cast<int>(pp % npx);
@@ -300,7 +328,7 @@ pair_setup_kernel(const PairSetup a) {
 }
 
 void launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
-    pair_setup_kernel<<<static_cast<unsigned>(static_cast<long>(a.n_pairs) * a.h * a.w), 128, 0, stream>>>(a);
+    launch_pdl(pair_setup_kernel, dim3(static_cast<unsigned>(static_cast<long>(a.n_pairs) * a.h * a.w)), dim3(128), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -309,6 +337,7 @@ void launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256)
 corr_pool_kernel(const float* __restrict__ L0, float* __restrict__ L1, float* __restrict__ L2, float* __restrict__ L3,
                  int h, int w) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int h1 = h / 2, w1 = w / 2, h2 = h1 / 2, w2 = w1 / 2, h3 = h2 / 2, w3 = w2 / 2;
     float* s1 = sm;
@@ -345,7 +374,7 @@ void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long row
         cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
-    corr_pool_kernel<<<static_cast<unsigned>(rows), 256, smem, stream>>>(L0, L1, L2, L3, h, w);
+    launch_pdl(corr_pool_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), smem, stream, L0, L1, L2, L3, h, w);
 }
 
 // ==========================================================================================
@@ -361,9 +390,10 @@ constexpr int kLkWin = 11;
 
 __global__ void __launch_bounds__(256)
 lookup_kernel(const LookupArgs a) {
+    pdl_enter();
     __shared__ float win[8][4][kLkWin * kLkWin + 3];
     __shared__ float frac[8][4][18];       // wE for the 9 x samples, wS for the 9 y samples
-    __shared__ int cell[8][4][18];         // window cell of floor(coordinate); kBadCell = non-finite coordinate
+    __shared__ int cell[8][4][18];         // window cell of floor(coordinate) (y cells pre-multiplied by the window pitch)
     constexpr int kBadCell = -100000;
     const int npx = a.h * a.w;
     const int wib = threadIdx.x >> 5;
@@ -375,15 +405,30 @@ lookup_kernel(const LookupArgs a) {
     const float cx = a.coords1[pp * 2], cy = a.coords1[pp * 2 + 1];
     __half* out = a.corr16 + pp * 328;
 
+    // level-independent index maps of this lane: window elements e = lane + 32k, outputs o = lane + 32k
+    int ewy[4], ewx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        ewy[k] = e / kLkWin;
+        ewx[k] = e - ewy[k] * kLkWin;
+    }
+    int oi[3], oj[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int o = lane + 32 * k;
+        oi[k] = o / 9;
+        oj[k] = o - oi[k] * 9;
+    }
     {
         int hl = a.h, wl = a.w;
         float div = 1.0f;
+        const bool isx = lane < 9;
+        const int kk = isx ? lane : lane - 9;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             // the 18 sample coordinates of this level: lanes 0..8 -> x offsets -4..4, lanes 9..17 -> y offsets
-            const bool isx = lane < 9;
-            const int k = isx ? lane : lane - 9;
-            const float c = (isx ? cx : cy) / div + static_cast<float>(k - 4);
+            const float c = (isx ? cx : cy) / div + static_cast<float>(kk - 4);
             const int size = isx ? wl : hl;
             const float pos = roundtrip_div(c, static_cast<float>(size - 1));
             const float pf = floorf(pos);
@@ -395,14 +440,19 @@ lookup_kernel(const LookupArgs a) {
             const bool all_fin = __all_sync(0xffffffffu, fin || lane >= 18);
             if (lane < 18) {
                 frac[wib][l][lane] = pos - pf;
-                cell[wib][l][lane] = all_fin ? cell_abs - (isx ? X0 : Y0) : kBadCell;
+                const int rel = cell_abs - (isx ? X0 : Y0);
+                const bool inside = rel >= 0 && rel < kLkWin - 1;
+                // cells outside the staged window can only see zeros: point them at the zero slot (see below)
+                cell[wib][l][lane] = !all_fin ? kBadCell : (inside ? (isx ? rel : rel * kLkWin) : -1);
             }
             const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
-            for (int e = lane; e < kLkWin * kLkWin; e += 32) {
-                const int wy = e / kLkWin, wx = e - wy * kLkWin;
-                const int gx = X0 + wx, gy = Y0 + wy;
-                win[wib][l][e] = (all_fin && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
-                                     ? __ldg(base + static_cast<long>(gy) * wl + gx) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (lane + 32 * k < kLkWin * kLkWin) {
+                    const int gx = X0 + ewx[k], gy = Y0 + ewy[k];
+                    win[wib][l][lane + 32 * k] = (all_fin && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
+                                                     ? __ldg(base + static_cast<long>(gy) * wl + gx) : 0.0f;
+                }
             }
             hl >>= 1; wl >>= 1; div *= 2.0f;
         }
@@ -411,47 +461,51 @@ lookup_kernel(const LookupArgs a) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const float* W = win[wib][l];
-        for (int o = lane; o < 81; o += 32) {
-            const int i = o / 9, j = o - i * 9;          // i: x offset index, j: y offset index
-            const int wx = cell[wib][l][i], wy = cell[wib][l][9 + j];
-            float r;
-            if (wx == kBadCell) {
-                r = NAN;
-            } else {
-                const float wE = frac[wib][l][i], wW = 1.0f - wE, wS = frac[wib][l][9 + j], wN = 1.0f - wS;
-                float vnw = 0.f, vne = 0.f, vsw = 0.f, vse = 0.f;
-                if (wx >= 0 && wx < kLkWin - 1 && wy >= 0 && wy < kLkWin - 1) {
-                    const float* q = W + wy * kLkWin + wx;
-                    vnw = q[0]; vne = q[1]; vsw = q[kLkWin]; vse = q[kLkWin + 1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (lane + 32 * k < 81) {
+                const int wx = cell[wib][l][oi[k]], wyo = cell[wib][l][9 + oj[k]];
+                float r;
+                if (wx == kBadCell) {
+                    r = NAN;
+                } else if (wx < 0 || wyo < 0) {
+                    r = 0.0f;
+                } else {
+                    const float wE = frac[wib][l][oi[k]], wS = frac[wib][l][9 + oj[k]];
+                    const float* q = W + wyo + wx;
+                    const float vnw = q[0], vne = q[1], vsw = q[kLkWin], vse = q[kLkWin + 1];
+                    // same blend as the oracle up to rounding (the result is rounded to fp16 anyway)
+                    const float top = fmaf(wE, vne - vnw, vnw), bot = fmaf(wE, vse - vsw, vsw);
+                    r = fmaf(wS, bot - top, top);
                 }
-                r = (wW * wN) * vnw;
-                r = r + (wE * wN) * vne;
-                r = r + (wW * wS) * vsw;
-                r = r + (wE * wS) * vse;
+                out[l * 81 + lane + 32 * k] = __float2half_rn(r);
             }
-            out[l * 81 + o] = __float2half_rn(r);
         }
     }
     if (lane < 4) out[324 + lane] = __float2half_rn(0.0f);
     // flow = coords1 - coords0 (core/raft.py:179); 7x7x2 zero-padded neighbourhood for convf1
     const long pbase = pp - n;
     __half* fp = a.flowpatch16 + pp * 104;
-    for (int k = lane; k < 104; k += 32) {
-        float v = 0.0f;
-        if (k < 98) {
-            const int c = k & 1, kx = (k >> 1) % 7, ky = (k >> 1) / 7;
-            const int yy = y + ky - 3, xx = x + kx - 3;
-            if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
-                v = a.coords1[(pbase + static_cast<long>(yy) * a.w + xx) * 2 + c] - static_cast<float>(c == 0 ? xx : yy);
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+        const int k = lane + 32 * k4;
+        if (k < 104) {
+            float v = 0.0f;
+            if (k < 98) {
+                const int c = k & 1, t = k >> 1, ky = t / 7, kx = t - ky * 7;
+                const int yy = y + ky - 3, xx = x + kx - 3;
+                if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
+                    v = a.coords1[(pbase + static_cast<long>(yy) * a.w + xx) * 2 + c] - static_cast<float>(c == 0 ? xx : yy);
+            }
+            fp[k] = __float2half_rn(v);
         }
-        fp[k] = __float2half_rn(v);
     }
     if (lane < 2) a.X[pp * 512 + 382 + lane] = __float2half_rn((lane == 0 ? cx : cy) - static_cast<float>(lane == 0 ? x : y));
 }
 
 void launch_lookup(const LookupArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    lookup_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(a);
+    launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -459,6 +513,7 @@ void launch_lookup(const LookupArgs& a, cudaStream_t stream) {
 // ==========================================================================================
 __global__ void __launch_bounds__(256)
 ou_pack_kernel(const OuPackArgs a) {
+    pdl_enter();
     const int npx = a.h * a.w;
     const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
@@ -481,7 +536,7 @@ ou_pack_kernel(const OuPackArgs a) {
 
 void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    ou_pack_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(a);
+    launch_pdl(ou_pack_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -491,6 +546,7 @@ void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
 // ==========================================================================================
 __global__ void __launch_bounds__(256)
 upsample_kernel(const UpsampleArgs a) {
+    pdl_enter();
     const int npx = a.h * a.w;
     const long pp = static_cast<long>(blockIdx.x) * 4 + (threadIdx.x >> 6);
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
@@ -542,7 +598,7 @@ upsample_kernel(const UpsampleArgs a) {
 
 void launch_upsample(const UpsampleArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    upsample_kernel<<<static_cast<unsigned>((total + 3) / 4), 256, 0, stream>>>(a);
+    launch_pdl(upsample_kernel, dim3(static_cast<unsigned>((total + 3) / 4)), dim3(256), 0, stream, a);
 }
 
 }  // namespace mftb

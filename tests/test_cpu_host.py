@@ -182,6 +182,7 @@ def test_tracker_bookkeeping(direction, monkeypatch):
         slots = [m['slot'] for m in trk.memory.values()]
         assert len(set(slots)) == len(slots) and not (set(slots) & set(trk._free_slots))
         assert tuple(meta.result.flow.shape) == (2, 8, 8)
+        assert len(trk._pool.free) >= 4                 # dropped results hand their pinned slot back
     assert [len(c[0]) for c in calls[:5]] == [1, 2, 3, 3, 4] and len(calls[40][0]) == 7
 
 
