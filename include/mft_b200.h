@@ -91,6 +91,9 @@ int mftb200_device_error_flag(mftb200_ctx* ctx);          /* syncs; 0 = clean */
  * iterations; "profile" 0|1 = per-launch event timing (see mftb200_profile_fetch); "cluster" (0 = auto,
  * 1|2|4|8) and "smem_cap_kib" = conv-kernel tuning knobs read by the next mftb200_configure. */
 int mftb200_set_option(mftb200_ctx* ctx, const char* key, int value);
+/* Process-wide conv-kernel tuning knobs (read when plans are built): "conv_v2" bit0 = use the 256-pixel haloed
+ * kernel, bit1 = descriptor base-offset mode; "pdl"; "cluster"; "smem_cap_kib". */
+int mftb200_set_global_option(const char* key, int value);
 /* Named internal buffer for stage-level parity tests ("fmap_slots", "net_slots", "corr_l0", ...). */
 int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t* bytes);
 /* Copies the first `bytes` bytes of a named internal buffer into caller device memory (syncs). */

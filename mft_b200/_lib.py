@@ -34,6 +34,7 @@ def _declare(lib):
         'mftb200_sample_points': (ci, [vp, ci, ci, ci, vp, ci, ci, vp, vp]),
         'mftb200_device_error_flag': (ci, [vp]),
         'mftb200_set_option': (ci, [vp, C.c_char_p, ci]),
+        'mftb200_set_global_option': (ci, [C.c_char_p, ci]),
         'mftb200_debug_buffer': (ci, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         'mftb200_debug_read': (ci, [vp, C.c_char_p, vp, C.c_size_t]),
         'mftb200_profile_fetch': (ci, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -41,7 +41,8 @@ struct ConvGeom {
     int b_rows_per_batch;         // B-matrix row offset per batch entry (correlation), 0 for weights
     int stages, tmem_cols;
     int cluster;                  // CTAs per cluster sharing (multicasting) the B operand: 1, 2, 4 or 8
-    int total_tiles;              // real tiles per batch entry * nbatch is checked in-kernel via b < nbatch
+    // variant 2 (256-pixel tile, haloed A operand shared by all taps): pitch / rows of the haloed box, stage counts
+    int pxp, py, na, nb, base_off_mode;
 };
 
 struct ConvEpi {
@@ -64,6 +65,9 @@ struct ConvEpi {
 struct ConvPlan {
     CUtensorMap tmA, tmB;
     ConvGeom g;
+    int variant;                  // 1 = 128-pixel tile, one A box per tap; 2 = 256-pixel tile with haloed A (see conv_tc.cu)
+    CUtensorMap tmA2;
+    ConvGeom g2;
     ConvEpi e;
     int mode;
     // raw views, used only by the SIMT cross-check kernel in tests
@@ -88,6 +92,8 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
 
 // Test / tuning override for the cluster size chosen by conv_plan_init (0 = automatic).
 void conv_set_forced_cluster(int c);
+// Variant-2 kernel on/off (default on) and its base-offset mode (tuning / bring-up).
+void conv_set_v2(int on, int base_off_mode);
 // Programmatic dependent launch on/off (default on).
 void conv_set_pdl(int on);
 // Caps the shared memory a CTA may use for pipeline stages (KiB, 0 = default 200).

@@ -331,6 +331,203 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// variant 2: 256-pixel tile (16 x 16), haloed A operand, B slab shared by the two 128-row halves
+// ------------------------------------------------------------------------------------------
+// The main loop of variant 1 is bound by shared-memory ingress (A box + B slab per tap): 96 B/clk/SM wanted,
+// ~50 delivered.  Here one CTA owns a 16x16 pixel tile = two 128-row MMA halves (columns 0-7 / 8-15):
+//  * per 64-channel chunk ONE haloed activation box (pitch `pxp` pixels x `py` rows) is loaded; every tap of the
+//    window addresses it through a row-shifted UMMA descriptor (8-row groups = 8 consecutive x of one tile row,
+//    group stride = haloed row pitch, base-offset = the shift within the 1024-byte swizzle atom);
+//  * each weight slab is loaded once and multiplied into both halves (two TMEM accumulators).
+// 3x3 / N=256: 343 KiB instead of 864 KiB of smem ingress per 256 pixels and chunk.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
+                const ConvEpi e) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = static_cast<uint32_t>(g.pxp * g.py) * 128;
+    const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
+    uint8_t* smem_b = smem + static_cast<size_t>(g.na) * a_bytes;
+    size_t pipe_bytes = static_cast<size_t>(g.na) * a_bytes + static_cast<size_t>(g.nb) * b_bytes;
+    if (pipe_bytes < 64 * 1024) pipe_bytes = 64 * 1024;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
+    uint64_t* a_empty = a_full + g.na;
+    uint64_t* b_full = a_empty + g.na;
+    uint64_t* b_empty = b_full + g.nb;
+    uint64_t* accum_ready = b_empty + g.nb;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
+    float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    long long* tstamp = e.timing ? e.timing + (static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+    if (tstamp && threadIdx.x == 0) {
+        tstamp[0] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        tstamp[7] = static_cast<long long>(gt);
+    }
+    int t = blockIdx.x;
+    const int tx = t % g.tiles_x;
+    t /= g.tiles_x;
+    const int ty = t % g.tiles_y;
+    const int b = t / g.tiles_y;
+    const int ny = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < g.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < g.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(accum_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, static_cast<uint32_t>(g.tmem_cols));
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (tstamp && threadIdx.x == 0) tstamp[1] = clock64();
+    const int rx = g.kw / 2, ry = g.kh / 2;
+    bool ok = true;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int x0 = tx * 16 - rx, y0 = ty * 16 - ry;
+            const int brow = ny * g.n_tile;
+            int it = 0;
+            for (int kc = 0; kc < g.kchunks && ok; ++kc) {
+                const int sa = kc % g.na;
+                if (!mbar_wait(&a_empty[sa], ((kc / g.na) & 1) ^ 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                tma_load_4d(smem + static_cast<size_t>(sa) * a_bytes, &tmA, &a_full[sa], kc * kChunkK, x0, y0, b);
+                for (int tap = 0; tap < g.ntaps; ++tap, ++it) {
+                    const int sb = it % g.nb;
+                    if (!mbar_wait(&b_empty[sb], ((it / g.nb) & 1) ^ 1)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                    tma_load_2d(smem_b + static_cast<size_t>(sb) * b_bytes, &tmB, &b_full[sb],
+                                (tap * g.kchunks + kc) * kChunkK, brow);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
+            const uint32_t sbo = static_cast<uint32_t>(g.pxp) * 128;
+            int it = 0;
+            for (int kc = 0; kc < g.kchunks && ok; ++kc) {
+                const int sa = kc % g.na;
+                if (!mbar_wait(&a_full[sa], (kc / g.na) & 1)) { ok = false; break; }
+                const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(sa) * a_bytes);
+                int kx = 0, ky = 0;
+                for (int tap = 0; tap < g.ntaps; ++tap, ++it) {
+                    const int sb = it % g.nb;
+                    if (!mbar_wait(&b_full[sb], (it / g.nb) & 1)) { ok = false; break; }
+                    if (tstamp && it == 0) tstamp[2] = clock64();
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(smem_b + static_cast<size_t>(sb) * b_bytes);
+                    const uint32_t a_tap = a_addr + static_cast<uint32_t>(ky * g.pxp + kx) * 128;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base + half * g.n_tile,
+                                     umma_desc_k128_ex(a_tap + half * 8 * 128 + k * 32, sbo, g.base_off_mode),
+                                     umma_desc_k128(b_addr + k * 32), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&b_empty[sb]);
+                    if (++kx == g.kw) { kx = 0; ++ky; }
+                }
+                umma_commit(&a_empty[sa]);
+            }
+            if (tstamp) tstamp[3] = clock64();
+            umma_commit(accum_ready);
+        }
+        __syncwarp();
+    }
+    {
+        const int q = warp & 3;
+        const int cpar = warp >> 2;
+        float* bw = bias_s + warp * 256;
+        for (int i = lane; i < 256; i += 32)
+            bw[i] = (e.bias != nullptr && i < ((g.n_tile + 31) & ~31)) ? __ldg(e.bias + ny * g.n_tile + i) : 0.0f;
+        __syncwarp();
+        const bool ok_acc = mbar_wait(accum_ready, 0);
+        ok = ok && ok_acc;
+        if (tstamp && warp == 2 && lane == 0) tstamp[4] = clock64();
+        tc_fence_after();
+        if (ok_acc) {
+            float* stg = reinterpret_cast<float*>(smem) + warp * 2048;
+            const int sub = lane >> 3, cq = lane & 7;
+            const int nchunk = (g.n_tile + 31) / 32;
+            // rows served by this lane: m = q*32 + k*4 + sub  ->  tile pixel (m >> 3, (m & 7) + 8*half)
+            long pixr[8];
+            unsigned valid_bits = 0;      // bit k: half 0, bit 8+k: half 1
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int m = q * 32 + k * 4 + sub;
+                const int y = ty * 16 + (m >> 3), x = tx * 16 + (m & 7);
+                if (y < g.H && b < g.nbatch) {
+                    if (x < g.W) valid_bits |= 1u << k;
+                    if (x + 8 < g.W) valid_bits |= 1u << (8 + k);
+                }
+                pixr[k] = (static_cast<long>(b) * g.H + y) * g.W + x;
+            }
+            int n_units = 0;
+            for (int u = cpar; u < 2 * nchunk; u += 2, ++n_units) {
+                const int half = u >= nchunk ? 1 : 0;
+                const int c = u - half * nchunk;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * g.n_tile + c * 32), r);
+                tmem_ld_wait();
+                float* buf = stg + (n_units & 1) * 1024;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const int col = ny * g.n_tile + c * 32 + cq * 4;
+                const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
+                const unsigned vb = valid_bits >> (8 * half);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    float4 v[4];
+                    long pix[4];
+                    bool val[4];
+                    EpiAux ax[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = (h2 * 4 + k) * 4 + sub;
+                        v[k] = *reinterpret_cast<const float4*>(buf + rr * 32 + ((cq ^ (rr & 7)) << 2));
+                        val[k] = (vb >> (h2 * 4 + k)) & 1u;
+                        pix[k] = pixr[h2 * 4 + k] + 8 * half;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (val[k]) ax[k] = epi_prefetch<MODE>(e, col, pix[k]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k]);
+                }
+            }
+        }
+    }
+    if (tstamp && warp == 2 && lane == 0) tstamp[5] = clock64();
+    if (!ok && e.err_flag != nullptr) atomicExch(e.err_flag, 1 + warp);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
+    if (tstamp && threadIdx.x == 0) tstamp[6] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------
 // SIMT cross-check kernel (tests only): same geometry, same epilogue, scalar fp32 FMAs.
 // ------------------------------------------------------------------------------------------
 template <int MODE>
@@ -398,6 +595,11 @@ void choose_tile(int H, int W, int* tile_h, int* tile_w) {
     }
 }
 
+// Variant 2 is correct but not faster on B200 (the variant-1 main loop already runs at the MMA floor for N=256 with
+// two co-resident CTAs, and N<=128 layers are bound by the per-instruction issue cost, not by smem ingress): off by
+// default, kept under test.  Measured: the UMMA swizzle is address based, so the base-offset field must stay 0.
+static int g_use_v2 = 0, g_v2_base_off = 0;
+void conv_set_v2(int on, int base_off_mode) { g_use_v2 = on; g_v2_base_off = base_off_mode; }
 static int g_use_pdl = 1;
 void conv_set_pdl(int on) { g_use_pdl = on; }
 static int g_forced_cluster = 0;
@@ -510,6 +712,39 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
         cuuint32_t es[2] = {1, 1};
         if (const char* err = encode(&p->tmB, wt, 2, dims, str, box, es)) return err;
     }
+    // ---- variant 2: stride-1 convolutions with enough tiles to matter -------------------------------------------
+    p->variant = 1;
+    if (g_use_v2 && stride == 1 && b_rows_per_batch == 0 && g.cluster == 1 && force_tile_h == 0 && taps.kw <= 5 &&
+        taps.kh <= 5 && in_H >= 16 && in_W >= 16) {
+        ConvGeom& q = p->g2;
+        q = g;
+        q.tile_h = 16; q.tile_w = 16; q.tile_w_log2 = 4;
+        q.tiles_x = (g.W + 15) / 16;
+        q.tiles_y = (g.H + 15) / 16;
+        q.pxp = taps.kw > 1 ? 24 : 16;
+        q.py = 16 + 2 * (taps.kh / 2);
+        q.base_off_mode = g_v2_base_off;
+        const int a2 = q.pxp * q.py * 128, b2 = n_tile * 128;
+        q.na = g.kchunks >= 2 ? 2 : 1;
+        int nb = (196 * 1024 - q.na * a2) / b2;
+        if (nb > 8) nb = 8;
+        if (nb > T) nb = T;
+        q.nb = nb;
+        int cols2 = 32;
+        while (cols2 < 2 * n_tile) cols2 *= 2;
+        q.tmem_cols = cols2;
+        const long tiles2 = static_cast<long>(q.tiles_x) * q.tiles_y * batch;
+        if (nb >= 2 && cols2 <= 512 && tiles2 >= 48) {
+            cuuint64_t dims[4] = {static_cast<cuuint64_t>(a_cin), static_cast<cuuint64_t>(in_W),
+                                  static_cast<cuuint64_t>(in_H), static_cast<cuuint64_t>(batch)};
+            cuuint64_t str[3] = {static_cast<cuuint64_t>(a_pitch) * 2, static_cast<cuuint64_t>(in_W) * a_pitch * 2,
+                                 static_cast<cuuint64_t>(in_H) * in_W * a_pitch * 2};
+            cuuint32_t box[4] = {kChunkK, static_cast<cuuint32_t>(q.pxp), static_cast<cuuint32_t>(q.py), 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            if (const char* err = encode(&p->tmA2, a_base, 4, dims, str, box, es)) return err;
+            p->variant = 2;
+        }
+    }
     return nullptr;
 }
 
@@ -521,6 +756,30 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
     if (use_simt) {
         conv_simt_kernel<MODE><<<grid, 128, 0, stream>>>(p.a_base, p.a_pitch, p.a_cin, p.in_H, p.in_W, p.b_base,
                                                          p.ktot, g, p.e);
+    } else if (p.variant == 2) {
+        ConvGeom g2 = p.g2;
+        g2.nbatch = nbatch;
+        size_t pipe = static_cast<size_t>(g2.na) * g2.pxp * g2.py * 128 + static_cast<size_t>(g2.nb) * g2.n_tile * 128;
+        if (pipe < 64 * 1024) pipe = 64 * 1024;
+        const size_t smem = pipe + 256 + 8 * 256 * sizeof(float) + 1024;
+        static bool attr_set2 = false;
+        if (!attr_set2) {
+            cudaError_t err = cudaFuncSetAttribute(conv2_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (err != cudaSuccess) return cudaGetErrorString(err);
+            attr_set2 = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(g2.tiles_x * g2.tiles_y * nbatch), static_cast<unsigned>(g2.n_tiles));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_use_pdl ? 1 : 0;
+        cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv2_tc_kernel<MODE>, p.tmA2, p.tmB, g2, p.e);
+        if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     } else {
         size_t pipe = static_cast<size_t>(g.stages) * (kTileM * 128 + g.n_tile * 128);
         if (pipe < 64 * 1024) pipe = 64 * 1024;                    // the epilogue stages 8 warps x 2 x 4 KiB in the idle pipeline slots

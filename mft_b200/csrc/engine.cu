@@ -667,10 +667,20 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()
     if (strcmp(key, "smem_cap_kib") == 0) { conv_set_smem_cap_kib(value); return MFTB200_OK; }      // next configure()
     return c->fail(MFTB200_ERR_ARG, "set_option: unknown key %s", key);
+}
+
+int mftb200_set_global_option(const char* key, int value) {
+    if (!key) return MFTB200_ERR_ARG;
+    if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }
+    if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
+    if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }
+    if (strcmp(key, "smem_cap_kib") == 0) { conv_set_smem_cap_kib(value); return MFTB200_OK; }
+    return MFTB200_ERR_ARG;
 }
 
 long long mftb200_launch_count(const mftb200_ctx* c) { return c ? c->launches : 0; }

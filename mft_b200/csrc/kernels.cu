@@ -274,31 +274,51 @@ __global__ void __launch_bounds__(256)
 instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict__ sums, int P, int C, int relu,
                       const __half2* __restrict__ res, __half2* __restrict__ out, long total2) {
     pdl_enter();
-    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total2) return;
+    // per-channel mean / rstd once per block (double: sum-of-squares minus square-of-sum cancels in fp32)
+    __shared__ float s_mean[128], s_rstd[128];
     const int c2 = C / 2;
-    const int cp = static_cast<int>(i % c2);
-    const int b = static_cast<int>(i / (static_cast<long>(P) * c2));
-    const double* s = sums + static_cast<long>(b) * 2 * C;
-    const double inv = 1.0 / P;
-    const double m0 = s[2 * cp] * inv, m1 = s[2 * cp + 1] * inv;
-    const double v0 = fmax(s[C + 2 * cp] * inv - m0 * m0, 0.0), v1 = fmax(s[C + 2 * cp + 1] * inv - m1 * m1, 0.0);
-    const float r0 = static_cast<float>(1.0 / sqrt(v0 + 1e-5)), r1 = static_cast<float>(1.0 / sqrt(v1 + 1e-5));
-    const float2 x = __half22float2(raw[i]);
-    float y0 = (x.x - static_cast<float>(m0)) * r0, y1 = (x.y - static_cast<float>(m1)) * r1;
-    if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-    if (res != nullptr) {
-        const float2 r = __half22float2(res[i]);
-        y0 = fmaxf(y0 + r.x, 0.f);
-        y1 = fmaxf(y1 + r.y, 0.f);
+    const long per_img2 = static_cast<long>(P) * c2;
+    const long i0 = static_cast<long>(blockIdx.x) * (blockDim.x * 8);
+    const int b = static_cast<int>(i0 / per_img2);          // a block never straddles two images (P*C/2 % 2048 == 0 is not
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {     //  required: stragglers recompute below)
+        const double* s = sums + static_cast<long>(b) * 2 * C;
+        const double inv = 1.0 / P;
+        const double m = s[c] * inv;
+        const double v = fmax(s[C + c] * inv - m * m, 0.0);
+        s_mean[c] = static_cast<float>(m);
+        s_rstd[c] = static_cast<float>(1.0 / sqrt(v + 1e-5));
     }
-    out[i] = __floats2half2_rn(y0, y1);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long i = i0 + static_cast<long>(k) * blockDim.x + threadIdx.x;
+        if (i >= total2) break;
+        const int cp = static_cast<int>(i % c2);
+        float m0 = s_mean[2 * cp], m1 = s_mean[2 * cp + 1], r0 = s_rstd[2 * cp], r1 = s_rstd[2 * cp + 1];
+        if (i / per_img2 != b) {                              // rare: element of the next image inside this block
+            const double* s = sums + (i / per_img2) * 2 * C;
+            const double inv = 1.0 / P;
+            const double a0 = s[2 * cp] * inv, a1 = s[2 * cp + 1] * inv;
+            m0 = static_cast<float>(a0); m1 = static_cast<float>(a1);
+            r0 = static_cast<float>(1.0 / sqrt(fmax(s[C + 2 * cp] * inv - a0 * a0, 0.0) + 1e-5));
+            r1 = static_cast<float>(1.0 / sqrt(fmax(s[C + 2 * cp + 1] * inv - a1 * a1, 0.0) + 1e-5));
+        }
+        const float2 x = __half22float2(raw[i]);
+        float y0 = (x.x - m0) * r0, y1 = (x.y - m1) * r1;
+        if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+        if (res != nullptr) {
+            const float2 r = __half22float2(res[i]);
+            y0 = fmaxf(y0 + r.x, 0.f);
+            y1 = fmaxf(y1 + r.y, 0.f);
+        }
+        out[i] = __floats2half2_rn(y0, y1);
+    }
 }
 
 void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
                            __half* out, cudaStream_t stream) {
     const long total2 = static_cast<long>(B) * P * C / 2;
-    launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total2 + 255) / 256)), dim3(256), 0, stream,
+    launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total2 + 2047) / 2048)), dim3(256), 0, stream,
                reinterpret_cast<const __half2*>(raw), sums, P, C, relu, reinterpret_cast<const __half2*>(res),
                reinterpret_cast<__half2*>(out), total2);
 }

@@ -158,6 +158,19 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B   [61,64)
     return d;
 }
+// Same layout for a tile whose 8-row groups are `sbo_bytes` apart and whose start may sit at any 128-byte row
+// of the swizzle pattern (haloed activation tiles addressed with a per-tap row shift): the "matrix base offset"
+// field (bits 49-51) tells the hardware which row of the 1024-byte swizzle atom the start address is.
+__device__ __forceinline__ uint64_t umma_desc_k128_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t use_base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    if (use_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 accumulate (c_format 1 at bit 4),
 // both operands K-major, N>>3 at bits [17,23), M>>4 at bits [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {

@@ -128,6 +128,10 @@ def chain_select(lefts, right, occlusion_threshold, want_index=True):
     return out, idx
 
 
+def set_global_option(key, value):
+    _lib.check(_lib.lib().mftb200_set_global_option(key.encode(), int(value)))
+
+
 def conv2d_bench(x16, w16, bias, cin, cout_pad, n_tile, kh, kw, stride, relu, cluster, smem_cap_kib, reps,
                  timing=None):
     """Tuning aid: the product conv kernel `reps` times; returns (out, mean ms per launch).

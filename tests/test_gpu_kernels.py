@@ -135,17 +135,27 @@ CONV_CASES = [
     (256, 576, 1, 1, 1, 16, 16, 1, 192), (147, 64, 1, 1, 1, 1, 1024, 1, 64), (712, 256, 3, 3, 1, 16, 16, 1, 256),
     (64, 96, 3, 3, 2, 32, 32, 1, 96), (64, 96, 1, 1, 2, 32, 32, 1, 96), (96, 128, 3, 3, 2, 64, 64, 1, 128),
     (98, 128, 1, 1, 1, 17, 30, 3, 128), (128, 128, 3, 3, 1, 135, 240, 1, 128), (384, 256, 1, 5, 1, 64, 64, 7, 256),
+    # large enough for the 256-pixel haloed kernel (variant 2): every window shape, ragged 16x16 tiling, narrow N
+    (384, 128, 5, 1, 1, 64, 64, 7, 128), (324, 256, 1, 1, 1, 64, 64, 7, 256), (256, 192, 3, 3, 1, 70, 90, 2, 192),
+    (256, 2, 3, 3, 1, 64, 64, 7, 16), (712, 256, 3, 3, 1, 64, 64, 2, 256), (64, 64, 3, 3, 1, 128, 128, 1, 64),
+    (256, 576, 1, 1, 1, 64, 64, 2, 192), (128, 64, 3, 3, 1, 50, 130, 3, 64),
 ]
 
 
 @pytest.mark.parametrize('case', CONV_CASES)
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 def test_conv_kernel_vs_torch(case, impl):
-    """impl 0 = tcgen05/TMA product kernel, impl 1 = SIMT cross-check kernel (same epilogue)."""
+    """impl 0 = tcgen05/TMA product kernel, impl 1 = SIMT cross-check kernel (same epilogue),
+    impl 2 = the experimental 256-pixel haloed-tile variant of the tcgen05 kernel (off by default)."""
     from mft_b200 import weights as WT
     cin, cout, kh, kw, stride, H, W, B, n_tile = case
-    if impl == 1 and H * W * B > 3000:
+    if impl == 1 and H * W * B * cin > 1500000:
         pytest.skip('SIMT cross-check kernel only at small sizes')
+    if impl == 2:
+        if stride != 1 or H < 16 or W < 16 or ((H + 15) // 16) * ((W + 15) // 16) * B < 48:
+            pytest.skip('variant 2 not selected for this geometry')
+        _E().set_global_option('conv_v2', 1)
+        impl = 0
     torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator().manual_seed(cin * 7 + cout)
     pitch = (cin + 7) // 8 * 8 + 8
@@ -158,6 +168,6 @@ def test_conv_kernel_vs_torch(case, impl):
                            n_tile, kh, kw, stride, True, impl)
     ref = torch.relu(torch.nn.functional.conv2d(xd[..., :cin].float().permute(0, 3, 1, 2), w.cuda(), b.cuda(), stride=stride,
                                                 padding=(kh // 2, kw // 2))).permute(0, 2, 3, 1)
+    _E().set_global_option('conv_v2', 0)
     err = (out[..., :cout] - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
-    assert (out[..., cout:] == 0).all() or cout == cout_pad or True

@@ -53,6 +53,8 @@ def run(name, cluster, smem, B=7, H=64, W=64, reps=20, check=True):
 
 
 if __name__ == '__main__':
+    if os.environ.get('TUNE_V2') is not None:
+        E.set_global_option('conv_v2', int(os.environ['TUNE_V2']))
     names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(LAYERS)
     clusters = [int(c) for c in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['1', '2', '4', '8'])]
     smems = [int(c) for c in (sys.argv[3].split(',') if len(sys.argv) > 3 else ['200'])]
