@@ -203,11 +203,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int x0 = g.stride * tx * g.tile_w;
             const int y0 = g.stride * ty * g.tile_h;
             const int brow = b * g.b_rows_per_batch + ny * g.n_tile;
-            int kc = 0, kx = 0, ky = 0;
+            int kc = 0, kx = 0, ky = 0, s = 0;
+            uint32_t ph = 0;
             const int rx = g.kw / 2, ry = g.kh / 2;
             for (int it = 0; it < T; ++it) {
-                const int s = it % g.stages;
-                const uint32_t ph = (it / g.stages) & 1;
                 if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
                 uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
@@ -224,26 +223,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     kc = 0;
                     if (++kx == g.kw) { kx = 0; ++ky; }
                 }
+                if (++s == g.stages) { s = 0; ph ^= 1; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
+            // descriptors: constant high words, low word = (address >> 4) | LBO field; +2 per K=16 step (32 bytes)
+            const uint64_t d0 = umma_desc_k128(smem_u32(smem));
+            const uint32_t dhi = static_cast<uint32_t>(d0 >> 32);
+            uint32_t alo = static_cast<uint32_t>(d0);
+            const uint32_t alo0 = alo, stage_lo = stage_bytes >> 4, b_off_lo = a_bytes >> 4;
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < T; ++it) {
-                const int s = it % g.stages;
-                const uint32_t ph = (it / g.stages) & 1;
                 if (!mbar_wait(&full[s], ph)) { ok = false; break; }
                 if (tstamp && it == 0) tstamp[2] = clock64();
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16(tmem_base, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                             (it | k) != 0 ? 1u : 0u);
+                const uint32_t blo = alo + b_off_lo;
+                // (Measured: one CTA sustains one MMA per ~147 cycles whatever N is, and dealing the K steps to several
+                //  independent TMEM accumulators does not change that -- narrow-N layers need co-resident CTAs.)
+                umma_f16_lohi(tmem_base, alo, dhi, blo, dhi, idesc, it != 0 ? 1u : 0u);
+                umma_f16_lohi(tmem_base, alo + 2, dhi, blo + 2, dhi, idesc, 1u);
+                umma_f16_lohi(tmem_base, alo + 4, dhi, blo + 4, dhi, idesc, 1u);
+                umma_f16_lohi(tmem_base, alo + 6, dhi, blo + 6, dhi, idesc, 1u);
                 // slot reusable once these MMAs have read it (in every CTA that multicasts into it)
                 if (g.cluster > 1) umma_commit_mc(&empty[s], cmask); else umma_commit(&empty[s]);
+                alo += stage_lo;
+                if (++s == g.stages) { s = 0; ph ^= 1; alo = alo0; }
             }
             if (tstamp) tstamp[3] = clock64();
             umma_commit(accum_ready);     // accumulator complete
