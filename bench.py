@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                                          '-i', str(self.idx), '-lms', '50'], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -180,7 +180,7 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
     weights, wsrc = load_weights()
     tracker = make_tracker(weights)
-    n_frames = 1 + STEADY + 2 * (Wm + K) + 2
+    n_frames = 1 + STEADY + 2 * (Wm + K) + 6
     frames = list(synthetic_video(n_frames, H, W, seed=1234 + rank))
     dev_frames = [torch.from_numpy(f).cuda() for f in frames]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
@@ -244,10 +244,20 @@ def run_ours(args):
     # ---- live per-launch profile of one step (rank 0) ----------------------------------------------
     conv_ms = other_ms = 0.0
     conv_n = 0
+    zr_ms, zr_n = 0.0, 0
     if rank == 0:
+        from mft_b200 import weights as _w
         eng.set_option('profile', 1)
-        tracker.track(dev_frames[t], device_result=True)
+        reps = 3
+        for _ in range(reps):
+            tracker.track(dev_frames[t], device_result=True)
+            t += 1
+        for ms, kind, layer in eng.profile_steps():
+            if 0 <= layer < len(_w.LAYER_NAMES) and _w.LAYER_NAMES[layer].startswith('gru_zr'):
+                zr_ms += ms
+                zr_n += 1
         (conv_ms, other_ms), (conv_n, _) = eng.profile_fetch()
+        conv_ms, other_ms, conv_n = conv_ms / reps, other_ms / reps, conv_n // reps
         eng.set_option('profile', 0)
 
     if world > 1:
@@ -267,7 +277,16 @@ def run_ours(args):
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (fp16 runs at the bf16 rate)' if peaks else 'fallback 1400 TFLOP/s sustained'
     F = flops_per_frame(H, W)
-    achieved = F / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    family = F / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    # dominant kernel: the SepConvGRU z|r-gate convolution (conv_tc_kernel<EPI_GRU_ZR>): 24 launches per step, each
+    # M = 7*(H/8)*(W/8) pixel rows x K = 5 taps*384 ch x N = 256 gates
+    zr_flops = 2.0 * 7 * (H // 8) * (W // 8) * 1920 * 256
+    achieved = zr_flops / (zr_ms / zr_n * 1e-3) / 1e12 if zr_n else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_gru_zr.json')))['dram_bytes_per_launch']
+    except Exception:
+        pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -288,9 +307,13 @@ def run_ours(args):
         'e2e': {'value': world * K / e2e_s, 'unit': 'frames/s', 'h2d_bytes_per_step': H * W * 3, 'd2h_bytes_per_step': 16 * H * W},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': (achieved / peak_tf) if achieved else None, 'traffic': None,
-                     'kernel': 'conv_tc_kernel (tcgen05 implicit GEMM, all layers)', 'peak_source': peak_src,
-                     'flops_per_step': F, 'conv_launches_per_step': conv_n, 'conv_ms_per_step': conv_ms,
+                     'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic,
+                     'kernel': 'conv_tc_kernel<EPI_GRU_ZR> (tcgen05 implicit GEMM: SepConvGRU z|r gates, M=28672 K=1920 N=256)',
+                     'peak_source': peak_src, 'flops_per_launch': zr_flops, 'launches_per_step': zr_n // 3 if zr_n else 0,
+                     'us_per_launch': (zr_ms / zr_n * 1e3) if zr_n else None,
+                     'conv_family': {'achieved': family, 'frac': (family / peak_tf) if family else None,
+                                     'flops_per_step': F, 'launches_per_step': conv_n, 'ms_per_step': conv_ms,
+                                     'note': 'all tcgen05 conv/GEMM launches of one step, minimal algorithmic FLOPs (BASELINE.md)'},
                      'other_kernels_ms_per_step': other_ms},
         'clocks': clocks,
     }

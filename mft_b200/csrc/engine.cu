@@ -74,11 +74,13 @@ struct mftb200_ctx {
     size_t corr_bytes[4] = {0, 0, 0, 0};
 
     std::vector<ConvPlan> plans;
+    std::vector<int> plan_layer;
     struct Step {
         std::function<const char*(mftb200_ctx*, cudaStream_t)> fn;
         int kind = 1;                       // 0 = tensor-core conv / GEMM launch, 1 = bandwidth-bound kernel(s)
         int lane = 0;                       // 0 = caller's stream, 1 = the engine's side stream (independent branch)
         int sync = 0;                       // 1 = fork (side stream waits for main), 2 = join (main waits for side)
+        int tag = -1;                       // conv layer id (enum Layer) or -1, reported by mftb200_profile_steps
         Step() = default;
         template <class F>
         Step(F f, int k = 1) : fn(std::move(f)), kind(k) {}
@@ -90,7 +92,7 @@ struct mftb200_ctx {
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
     std::vector<cudaEvent_t> prof_events;   // pairs
-    std::vector<int> prof_kinds;
+    std::vector<int> prof_kinds, prof_tags;
     int cur_slot = 0, cur_pairs = 0;
 
     int fail(int code, const char* fmt, ...) {
@@ -114,6 +116,7 @@ struct mftb200_ctx {
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
         plans.clear();
+        plan_layer.clear();
         enc_steps.clear(); pre_steps.clear(); iter_steps.clear(); final_steps.clear();
         configured = false;
     }
@@ -151,9 +154,11 @@ struct Builder {
         p.e.n_valid = cout_pad;
         p.e.err_flag = c->err_flag;
         c->plans.push_back(p);
+        c->plan_layer.push_back(layer >= 0 ? layer : 100);        // 100 = the all-pairs correlation GEMM
         return static_cast<int>(c->plans.size()) - 1;
     }
     ConvEpi& epi(int i) { return c->plans[i].e; }
+    mftb200_ctx::Step step(int plan_idx, bool batched_pairs);   // launch step tagged with the plan's layer id
     // conv with fp16 output
     int conv16(int layer, Act in, int batch, int stride, TapList taps, int n_tile, int relu, __half* out, int out_stride,
                int out_coff, int n_valid, const __half* res = nullptr, int res_stride = 0) {
@@ -179,6 +184,13 @@ mftb200_ctx::Step conv_step(int plan_idx, bool batched_pairs) {
     }, 0);
 }
 
+
+mftb200_ctx::Step Builder::step(int plan_idx, bool batched_pairs) {
+    mftb200_ctx::Step st = conv_step(plan_idx, batched_pairs);
+    if (plan_idx >= 0) st.tag = c->plan_layer[plan_idx];
+    return st;
+}
+
 const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb200_ctx::Step>& S, __half* const* E) {
     const bool inorm = (net == L_FNET);
     const int H2 = c->Hp / 2, W2 = c->Wp / 2, H4 = c->Hp / 4, W4 = c->Wp / 4, H8 = c->h, W8 = c->w;
@@ -199,10 +211,10 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb2
     {
         Act in{c->patches, 152, 147, 1, P2};
         if (inorm) {
-            S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 0, c->raw, 64, 0, 64), false));
+            S.push_back(B.step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 0, c->raw, 64, 0, 64), false));
             norm(c->raw, P2, 64, 1, nullptr, E[0]);
         } else {
-            S.push_back(conv_step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 1, E[0], 64, 0, 64), false));
+            S.push_back(B.step(B.conv16(net + E_CONV1, in, 1, 1, t1, 64, 1, E[0], 64, 0, 64), false));
         }
     }
     struct Blk { int c1, c2, ds, cin, cout, stride, Hin, Win; };
@@ -221,22 +233,22 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb2
         Act atmp{tmp, b.cout, b.cout, Ho, Wo};
         const __half* res = in;
         if (inorm) {
-            S.push_back(conv_step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
+            S.push_back(B.step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
             norm(c->raw, Po, b.cout, 1, nullptr, tmp);
             if (b.ds >= 0) {
-                S.push_back(conv_step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, c->raw2, b.cout, 0, b.cout), false));
+                S.push_back(B.step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, c->raw2, b.cout, 0, b.cout), false));
                 norm(c->raw2, Po, b.cout, 0, nullptr, xd);
                 res = xd;
             }
-            S.push_back(conv_step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
+            S.push_back(B.step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
             norm(c->raw, Po, b.cout, 1, res, out);
         } else {
-            S.push_back(conv_step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 1, tmp, b.cout, 0, b.cout), false));
+            S.push_back(B.step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 1, tmp, b.cout, 0, b.cout), false));
             if (b.ds >= 0) {
-                S.push_back(conv_step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, xd, b.cout, 0, b.cout), false));
+                S.push_back(B.step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, xd, b.cout, 0, b.cout), false));
                 res = xd;
             }
-            S.push_back(conv_step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 1, out, b.cout, 0, b.cout, res, b.cout), false));
+            S.push_back(B.step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 1, out, b.cout, 0, b.cout, res, b.cout), false));
         }
         cur ^= 1;
     }
@@ -261,6 +273,7 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb2
             cc->launches++;
             return conv_launch(p, 1, s, cc->conv_impl);
         }, 0));
+        S.back().tag = net + E_CONV2;
     }
     return B.err;
 }
@@ -284,7 +297,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             ConvEpi& e = B.epi(i);
             e.scale = 0.0625f; e.out32 = c->corr[0]; e.out32_stride = npx; e.out32_coff = 0; e.n_valid = npx;
         }
-        c->pre_steps.push_back(conv_step(i, true));
+        c->pre_steps.push_back(B.step(i, true));
     }
     c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         launch_corr_pool(cc->corr[0], cc->corr[1], cc->corr[2], cc->corr[3], static_cast<long>(cc->cur_pairs) * cc->npx,
@@ -314,14 +327,14 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     // motion encoder (update.py:152-160)
     // the correlation branch (caller's stream) and the flow branch (side stream) are independent until `conv`
     S.push_back(sync_step(1));
-    S.push_back(conv_step(B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
-    S.push_back(conv_step(B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
+    S.push_back(B.step(B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
+    S.push_back(B.step(B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
     S.back().lane = 1;
-    S.push_back(conv_step(B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
-    S.push_back(conv_step(B.conv16(L_CONVF2, a_f1, mp, 1, t3, 64, 1, c->cf, 256, 192, 64), true));
+    S.push_back(B.step(B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
+    S.push_back(B.step(B.conv16(L_CONVF2, a_f1, mp, 1, t3, 64, 1, c->cf, 256, 192, 64), true));
     S.back().lane = 1;
     S.push_back(sync_step(2));
-    S.push_back(conv_step(B.conv16(L_CONVM, a_cf, mp, 1, t3, 128, 1, c->X, 512, 256, 126), true));
+    S.push_back(B.step(B.conv16(L_CONVM, a_cf, mp, 1, t3, 128, 1, c->X, 512, 256, 126), true));
     // SepConvGRU (update.py:108-123): horizontal 1x5 then vertical 5x1
     for (int pass = 0; pass < 2; ++pass) {
         const TapList& tp = pass == 0 ? t15 : t51;
@@ -330,35 +343,35 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             ConvEpi& e = B.epi(izr);
             e.n_valid = 256; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 384;
         }
-        S.push_back(conv_step(izr, true));
+        S.push_back(B.step(izr, true));
         const int iq = B.conv(pass == 0 ? L_GRU_Q1 : L_GRU_Q2, a_qx, mp, 1, tp, 128, EPI_GRU_Q);
         if (iq >= 0) {
             ConvEpi& e = B.epi(iq);
             e.n_valid = 128; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 0;
         }
-        S.push_back(conv_step(iq, true));
+        S.push_back(B.step(iq, true));
     }
     // flow head (update.py:6-14) ; coords1 += delta_flow (core/raft.py:184)
-    S.push_back(conv_step(B.conv16(L_FH1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    S.push_back(B.step(B.conv16(L_FH1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
     {
         const int i = B.conv(L_FH2, a_fh, mp, 1, t3, 16, EPI_FLOW);
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
             e.n_valid = 2; e.coords1 = c->coords1; e.delta32 = c->delta32;
         }
-        S.push_back(conv_step(i, true));
+        S.push_back(B.step(i, true));
     }
 
     // ---- after the last iteration: mask head, OU head, convex upsampling ---------------------
     auto& Fz = c->final_steps;
-    Fz.push_back(conv_step(B.conv16(L_MASK1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    Fz.push_back(B.step(B.conv16(L_MASK1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
     {
         const int i = B.conv(L_MASK2, a_fh, mp, 1, t1, 192, EPI_F32);
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
             e.scale = 0.25f; e.out32 = c->mask32; e.out32_stride = 576; e.n_valid = 576;   // update.py:237
         }
-        Fz.push_back(conv_step(i, true));
+        Fz.push_back(B.step(i, true));
     }
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         OuPackArgs a{cc->X, cc->corr16, cc->coords1, cc->delta32, cc->oupack, cc->cur_pairs, cc->h, cc->w};
@@ -367,14 +380,14 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         return nullptr;
     });
     Act a_ou{c->oupack, 720, 712, h, w};
-    Fz.push_back(conv_step(B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    Fz.push_back(B.step(B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
     {
         const int i = B.conv(L_OU2, a_fh, mp, 1, t3, 16, EPI_F32);
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
             e.out32 = c->ou32; e.out32_stride = 4; e.n_valid = 3;
         }
-        Fz.push_back(conv_step(i, true));
+        Fz.push_back(B.step(i, true));
     }
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         UpsampleArgs a{cc->mask32, cc->coords1, cc->ou32, cc->out, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
@@ -410,6 +423,7 @@ int run_steps(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cudaStream_
             c->prof_events.push_back(a);
             c->prof_events.push_back(b);
             c->prof_kinds.push_back(st.kind);
+            c->prof_tags.push_back(st.tag);
             if (e) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
         } else if (const char* e = st.fn(c, s)) {
             return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
@@ -692,7 +706,7 @@ int mftb200_profile_steps(mftb200_ctx* c, float* ms, int* kinds, int max_steps, 
     *n_steps = n;
     for (int i = 0; i < n && i < max_steps; ++i) {
         cudaEventElapsedTime(&ms[i], c->prof_events[2 * i], c->prof_events[2 * i + 1]);
-        kinds[i] = c->prof_kinds[i];
+        kinds[i] = c->prof_kinds[i] | ((c->prof_tags[i] + 1) << 8);   // low byte: kind, upper bits: layer id + 1
     }
     return MFTB200_OK;
 }
@@ -713,6 +727,7 @@ int mftb200_profile_fetch(mftb200_ctx* c, double* ms_by_kind, long long* steps_b
     }
     c->prof_events.clear();
     c->prof_kinds.clear();
+    c->prof_tags.clear();
     return MFTB200_OK;
 }
 

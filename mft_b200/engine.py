@@ -87,12 +87,14 @@ class Engine:
         return [float(ms[0]), float(ms[1])], [int(n[0]), int(n[1])]
 
     def profile_steps(self, max_steps=4096):
-        """Per-step (ms, kind) in launch order since profiling was switched on."""
+        """Per-step (ms, kind, layer) in launch order since profiling was switched on; kind 0 = tensor-core
+        conv/GEMM, 1 = bandwidth-bound kernel(s); layer = index into weights.LAYER_NAMES, 100 = correlation
+        GEMM, -1 = not a conv."""
         ms = (C.c_float * max_steps)()
         kinds = (C.c_int * max_steps)()
         n = C.c_int(0)
         _lib.check(self.L.mftb200_profile_steps(self.ctx, ms, kinds, max_steps, C.byref(n)), self.ctx)
-        return [(float(ms[i]), int(kinds[i])) for i in range(min(n.value, max_steps))]
+        return [(float(ms[i]), int(kinds[i]) & 0xff, (int(kinds[i]) >> 8) - 1) for i in range(min(n.value, max_steps))]
 
     def launch_count(self):
         return int(self.L.mftb200_launch_count(self.ctx))

@@ -173,3 +173,17 @@ def test_tracker_vs_oracle_real_128(real_weights):
         if f'result_{i}' in g.files:
             epe_ref = np.sqrt(((got[:2] - g[f'result_{i}'][:2]) ** 2).sum(0))
             assert np.median(epe_ref) < 0.05
+
+
+def test_flow_sharding_two_gpus():
+    """per-timestep flow sharding + one all_gather per round, on 2 real GPUs (skipped on 1)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29611', os.path.join(root, 'tools', 'flow_shard_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'bit-identical' in r.stdout

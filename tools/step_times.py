@@ -27,7 +27,7 @@ for r in range(reps):
     eng.profile_fetch()
     eng.set_option('profile', 0)
     acc = [a + b[0] for a, b in zip(acc, st)] if acc else [b[0] for b in st]
-kinds = [k for _, k in st]
+kinds = [k for _, k, _ in st]
 ENC = ['patches'] + [f'fnet{i}' for i in range(100)]
 tot = sum(acc) / reps
 print(f'{len(acc)} steps, total {tot * 1e3:.1f} us (events add ~2-4 us per step)')
