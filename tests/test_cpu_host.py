@@ -245,3 +245,36 @@ def test_flow_sharding_world2_gloo_matches_single_process():
     assert got[0] == want and got[1] == want
     from mft_b200.dist import shard_items
     assert shard_items(10, 1, 4) == [1, 5, 9] and sorted(sum((shard_items(10, r, 4) for r in range(4)), [])) == list(range(10))
+
+
+def test_flow_cache_protocol_host_logic(monkeypatch):
+    """Cached pairs are not recomputed; only finite deltas are cached unless C.cache_delta_infinity (MFT.py:99,209-228)."""
+    deltas = [np.inf, 1, 2]
+    trk, eng, calls = _tracker_without_gpu(deltas, 1, 0, monkeypatch)
+
+    class Cache:
+        def __init__(self):
+            self.store, self.writes = {}, []
+
+        def read(self, l, r):
+            return self.store.get((l, r), (None, None, None))
+
+        def write(self, l, r, f, o, s):
+            self.writes.append((l, r))
+            self.store[(l, r)] = (f, o, s)
+    cache = Cache()
+    img = lambda i: np.full((8, 8, 3), i, np.uint8)
+    for rep in range(2):
+        trk.init(img(0), flow_cache=cache)
+        n0 = len(calls)
+        for t in range(1, 5):
+            trk.track(img(t))
+        pairs = [len(c[0]) for c in calls[n0:]]
+        # first pass computes every live chain; second pass only the (uncached) template chain
+        assert pairs == ([1, 2, 3, 3] if rep == 0 else [1, 1, 1, 1])
+    # (0,1) is computed under delta=inf (delta 1 collapses onto it, MFT.py:90) and is therefore not cached
+    assert sorted(set(cache.writes)) == [(1, 2), (1, 3), (2, 3), (2, 4), (3, 4)]
+    trk.C.cache_delta_infinity = True
+    trk.init(img(0), flow_cache=cache)
+    trk.track(img(1))
+    assert (0, 1) in cache.store

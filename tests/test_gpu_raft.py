@@ -187,3 +187,91 @@ def test_flow_sharding_two_gpus():
                         '--master-port', '29611', os.path.join(root, 'tools', 'flow_shard_check.py')], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'bit-identical' in r.stdout
+
+
+class _DictCache:
+    """Minimal FlowCache protocol (MFT/utils/io.py:655-698): read -> (flow, occl, sigma) or Nones; write."""
+
+    def __init__(self):
+        self.store, self.reads, self.hits, self.writes = {}, 0, 0, 0
+
+    def read(self, left_id, right_id):
+        self.reads += 1
+        if (left_id, right_id) in self.store:
+            self.hits += 1
+            return self.store[(left_id, right_id)]
+        return None, None, None
+
+    def write(self, left_id, right_id, flow, occl, sigma):
+        self.writes += 1
+        self.store[(left_id, right_id)] = (flow, occl, sigma)
+
+
+def _make_tracker(weights, deltas):
+    from mft_b200.config import Config
+    from mft_b200.MFT import MFT
+    from mft_b200.raft import RAFTWrapper
+    fc = Config(); fc.of_class = RAFTWrapper; fc.model = weights; fc.flow_iters = 12
+    C = Config(); C.flow_config = fc; C.deltas = deltas; C.occlusion_threshold = 0.02
+    return MFT(C)
+
+
+def test_backward_tracking_and_flow_cache(seeded_weights):
+    """time_direction=-1 (strided TAP-Vid eval) and the flow-cache protocol: a second pass over the same frames must be
+    served from the cache for every finite delta (inf is not cached, MFT.py:99) and reproduce the first bit for bit."""
+    from mft_b200.synth import synthetic_video
+    frames = list(synthetic_video(9, 128, 160, seed=21))
+    deltas = [np.inf, 1, 2, 4]
+    trk = _make_tracker(seeded_weights, deltas)
+    cache = _DictCache()
+    runs = []
+    for _ in range(2):
+        trk.init(frames[8], start_frame_i=8, time_direction=-1, flow_cache=cache)
+        out = []
+        for t in range(7, -1, -1):
+            meta = trk.track(frames[t], debug=True)
+            want = O.live_chains(deltas, t, 8, -1)
+            assert meta.used_deltas == [d for d, _ in want]
+            out.append(meta.result.packed().clone())
+        runs.append(out)
+    finite_pairs = sum(len([d for d, _ in O.live_chains(deltas, t, 8, -1) if np.isfinite(d)]) for t in range(7, -1, -1))
+    assert cache.writes == finite_pairs and cache.hits == finite_pairs
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+    assert all(torch.isfinite(a).all() for a in runs[0])
+
+
+@pytest.mark.parametrize('size', [(512, 512), (1080, 1920)])
+def test_known_motion_full_size(size, real_weights):
+    """BASELINE sizes with the shipped checkpoint: a pure integer translation of a textured frame must come back as that
+    flow (interior), a static pair as zero flow, with low sigma / occlusion -- size-independent properties (the CPU
+    oracle needs minutes and > 10 GB at 1080p)."""
+    from mft_b200.synth import synthetic_video
+    H, W = size
+    big = next(synthetic_video(1, H + 32, W + 32, seed=2))
+    a = np.ascontiguousarray(big[16:16 + H, 16:16 + W])
+    dx, dy = 5, -3
+    b = np.ascontiguousarray(big[16 - dy:16 - dy + H, 16 - dx:16 - dx + W])      # content moves by (+dx, +dy)
+    eng = _engine(real_weights, H, W, pairs=2, slots=3)
+    eng.encode_frame(a, 0); eng.encode_frame(b, 1)
+    out = eng.refine([0, 0], [1, 0]).cpu()
+    eng.check_device()
+    m = 48
+    inner = out[:, :, m:-m, m:-m]
+    assert (inner[0, 0] - dx).abs().median() < 0.05 and (inner[0, 1] - dy).abs().median() < 0.05
+    assert ((inner[0, 0] - dx).abs() < 0.5).float().mean() > 0.98
+    assert inner[1, :2].abs().max() < 0.25 and inner[1, :2].abs().median() < 0.02          # static pair -> zero flow
+    assert inner[:, 2].median() < 0.02 and torch.isfinite(out).all()
+
+
+def test_config4_shape_1024_32iters(seeded_weights):
+    """BASELINE configs[3] geometry: 1024x1024, 32 GRU iterations (2 pairs here): runs, finite, batch-independent."""
+    from mft_b200.synth import synthetic_video
+    frames = list(synthetic_video(3, 1024, 1024, seed=9))
+    eng = _engine(seeded_weights, 1024, 1024, pairs=2, slots=3, iters=32)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    both = eng.refine([0, 1], [2, 2]).clone()
+    eng.check_device()
+    assert torch.isfinite(both).all()
+    assert torch.equal(eng.refine([1], [2])[0], both[1])
