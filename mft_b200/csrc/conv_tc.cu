@@ -31,27 +31,29 @@ struct EpiAux {
     float4 a, b;
 };
 
+// Pixel indices are 32-bit everywhere except the correlation volume (pixel * N^2 overflows): `pix` stays 64-bit in
+// the signature but every mode other than EPI_F32 does its address arithmetic on the low 32 bits (M * stride < 2^31).
 template <int MODE>
 __device__ __forceinline__ EpiAux epi_prefetch(const ConvEpi& e, int col, long pix) {
     EpiAux x;
     x.a = make_float4(0.f, 0.f, 0.f, 0.f);
     x.b = x.a;
-    if (col >= e.n_valid) return x;
+    const uint32_t p32 = static_cast<uint32_t>(pix);
     if constexpr (MODE == EPI_F16) {
         if (e.res16 != nullptr && col + 4 <= e.n_valid) {
-            const uint2 rr = *reinterpret_cast<const uint2*>(e.res16 + pix * e.res_stride + e.res_coff + col);
+            const uint2 rr = *reinterpret_cast<const uint2*>(e.res16 + (p32 * e.res_stride + e.res_coff + col));
             const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
             const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
             x.a = make_float4(r0.x, r0.y, r1.x, r1.y);
         }
     } else if constexpr (MODE == EPI_GRU_ZR) {
-        if (col >= 128) x.a = *reinterpret_cast<const float4*>(e.h32 + pix * 128 + (col - 128));
+        if (col >= 128) x.a = *reinterpret_cast<const float4*>(e.h32 + (p32 * 128u + (col - 128)));
     } else if constexpr (MODE == EPI_GRU_Q) {
-        x.a = *reinterpret_cast<const float4*>(e.h32 + pix * 128 + col);
-        x.b = *reinterpret_cast<const float4*>(e.z32 + pix * 128 + col);
+        x.a = *reinterpret_cast<const float4*>(e.h32 + (p32 * 128u + col));
+        x.b = *reinterpret_cast<const float4*>(e.z32 + (p32 * 128u + col));
     } else if constexpr (MODE == EPI_FLOW) {
         if (col == 0) {
-            const float2 c = *reinterpret_cast<const float2*>(e.coords1 + pix * 2);
+            const float2 c = *reinterpret_cast<const float2*>(e.coords1 + p32 * 2u);
             x.a.x = c.x;
             x.a.y = c.y;
         }
@@ -67,14 +69,15 @@ __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) 
     return pk;
 }
 
+// `col` < n_valid is guaranteed by the caller; relu_lo = 0 (ReLU) or -inf (none) makes the activation branch-free.
 template <int MODE>
-__device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const float4 bb, const EpiAux& ax, int col, long pix) {
-    if (col >= e.n_valid) return;
+__device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const float4 bb, const EpiAux& ax, int col, long pix,
+                                          bool full, float relu_lo) {
     v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-    const bool full = col + 4 <= e.n_valid;
+    const uint32_t p32 = static_cast<uint32_t>(pix);
     if constexpr (MODE == EPI_F16) {
-        if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        __half* o = e.out16 + pix * e.out16_stride + e.out16_coff + col;
+        v.x = fmaxf(v.x, relu_lo); v.y = fmaxf(v.y, relu_lo); v.z = fmaxf(v.z, relu_lo); v.w = fmaxf(v.w, relu_lo);
+        __half* o = e.out16 + (p32 * e.out16_stride + e.out16_coff + col);
         if (full) {
             if (e.res16 != nullptr) {
                 v.x = fmaxf(v.x + ax.a.x, 0.f); v.y = fmaxf(v.y + ax.a.y, 0.f);
@@ -85,13 +88,13 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
             const float a[4] = {v.x, v.y, v.z, v.w};
             for (int j = 0; j < 4 && col + j < e.n_valid; ++j) {
                 float x = a[j];
-                if (e.res16 != nullptr) x = fmaxf(x + __half2float(e.res16[pix * e.res_stride + e.res_coff + col + j]), 0.f);
+                if (e.res16 != nullptr) x = fmaxf(x + __half2float(e.res16[p32 * e.res_stride + e.res_coff + col + j]), 0.f);
                 o[j] = __float2half_rn(x);
             }
         }
     } else if constexpr (MODE == EPI_F32) {
-        v.x *= e.scale; v.y *= e.scale; v.z *= e.scale; v.w *= e.scale;
-        if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        v.x = fmaxf(v.x * e.scale, relu_lo); v.y = fmaxf(v.y * e.scale, relu_lo);
+        v.z = fmaxf(v.z * e.scale, relu_lo); v.w = fmaxf(v.w * e.scale, relu_lo);
         float* o = e.out32 + pix * e.out32_stride + e.out32_coff + col;
         if (full && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
             *reinterpret_cast<float4*>(o) = v;
@@ -101,17 +104,17 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
         }
     } else if constexpr (MODE == EPI_CNET) {
         if (col < 128) {
-            *reinterpret_cast<float4*>(e.out32 + pix * 128 + col) = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+            *reinterpret_cast<float4*>(e.out32 + (p32 * 128u + col)) = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
         } else {
-            *reinterpret_cast<uint2*>(e.out16 + pix * 128 + (col - 128)) =
+            *reinterpret_cast<uint2*>(e.out16 + (p32 * 128u + (col - 128))) =
                 pack_half4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
         }
     } else if constexpr (MODE == EPI_GRU_ZR) {
         if (col < 128) {
-            *reinterpret_cast<float4*>(e.z32 + pix * 128 + col) =
+            *reinterpret_cast<float4*>(e.z32 + (p32 * 128u + col)) =
                 make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
         } else {
-            *reinterpret_cast<uint2*>(e.out16 + pix * e.out16_stride + e.out16_coff + (col - 128)) =
+            *reinterpret_cast<uint2*>(e.out16 + (p32 * e.out16_stride + e.out16_coff + (col - 128))) =
                 pack_half4(sigmoidf_(v.x) * ax.a.x, sigmoidf_(v.y) * ax.a.y, sigmoidf_(v.z) * ax.a.z, sigmoidf_(v.w) * ax.a.w);
         }
     } else if constexpr (MODE == EPI_GRU_Q) {
@@ -121,12 +124,12 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
         n.y = (1.0f - zv.y) * hv.y + zv.y * tanh_gate(v.y);
         n.z = (1.0f - zv.z) * hv.z + zv.z * tanh_gate(v.z);
         n.w = (1.0f - zv.w) * hv.w + zv.w * tanh_gate(v.w);
-        *reinterpret_cast<float4*>(e.h32 + pix * 128 + col) = n;
-        *reinterpret_cast<uint2*>(e.out16 + pix * e.out16_stride + e.out16_coff + col) = pack_half4(n.x, n.y, n.z, n.w);
+        *reinterpret_cast<float4*>(e.h32 + (p32 * 128u + col)) = n;
+        *reinterpret_cast<uint2*>(e.out16 + (p32 * e.out16_stride + e.out16_coff + col)) = pack_half4(n.x, n.y, n.z, n.w);
     } else if constexpr (MODE == EPI_FLOW) {
         if (col == 0) {
-            *reinterpret_cast<float2*>(e.delta32 + pix * 2) = make_float2(v.x, v.y);
-            *reinterpret_cast<float2*>(e.coords1 + pix * 2) = make_float2(ax.a.x + v.x, ax.a.y + v.y);
+            *reinterpret_cast<float2*>(e.delta32 + p32 * 2u) = make_float2(v.x, v.y);
+            *reinterpret_cast<float2*>(e.coords1 + p32 * 2u) = make_float2(ax.a.x + v.x, ax.a.y + v.y);
         }
     }
 }
@@ -305,6 +308,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (tt) tstamp[10 + (c >> 1) * 4] = clock64();
                 const int col = ny * g.n_tile + c * 32 + cq * 4;
                 const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
+                const bool col_ok = col < e.n_valid, full = col + 4 <= e.n_valid;
+                const float relu_lo = e.relu ? 0.0f : -INFINITY;
+                if (col_ok) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float4 v[4];
@@ -323,7 +329,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (val[k]) ax[k] = epi_prefetch<MODE>(e, col, pix[k]);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k]);
+                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k], full, relu_lo);
+                }
                 }
                 if (tt) tstamp[11 + (c >> 1) * 4] = clock64();
             }
@@ -504,6 +511,9 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int col = ny * g.n_tile + c * 32 + cq * 4;
                 const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
                 const unsigned vb = valid_bits >> (8 * half);
+                const bool col_ok = col < e.n_valid, full = col + 4 <= e.n_valid;
+                const float relu_lo = e.relu ? 0.0f : -INFINITY;
+                if (col_ok) {
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     float4 v[4];
@@ -522,7 +532,8 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if (val[k]) ax[k] = epi_prefetch<MODE>(e, col, pix[k]);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k]);
+                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k], full, relu_lo);
+                }
                 }
             }
         }
@@ -571,10 +582,12 @@ conv_simt_kernel(const __half* __restrict__ A, int a_pitch, int a_cin, int in_H,
         }
         for (int j = 0; j < 32; j += 4) {
             const int col = ny * g.n_tile + c0 + j;
+            if (col >= e.n_valid) continue;
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.bias != nullptr && col < e.n_valid) bb = *reinterpret_cast<const float4*>(e.bias + col);
+            if (e.bias != nullptr) bb = *reinterpret_cast<const float4*>(e.bias + col);
             const EpiAux ax = epi_prefetch<MODE>(e, col, pix);
-            epilogue4<MODE>(e, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), bb, ax, col, pix);
+            epilogue4<MODE>(e, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), bb, ax, col, pix,
+                            col + 4 <= e.n_valid, e.relu ? 0.0f : -INFINITY);
         }
     }
 }
