@@ -57,6 +57,8 @@ struct ConvEpi {
     float* z32;                   // GRU update gate scratch  [pixel][128]
     float* coords1;               // [pixel][2]
     float* delta32;               // [pixel][2]
+    double* stats;                // optional [2][n_valid] per-channel sum / sum of squares of the (pre-activation) outputs,
+                                  // accumulated with atomics: instance-norm statistics fused into the producing conv
     int* err_flag;
     long long* timing;            // optional per-CTA phase timestamps [cta][8] (tuning aid), nullptr in product runs
 };

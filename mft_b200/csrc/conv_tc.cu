@@ -149,12 +149,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     size_t pipe_bytes = static_cast<size_t>(g.stages) * stage_bytes;
-    if (pipe_bytes < 64 * 1024) pipe_bytes = 64 * 1024;            // room for the epilogue staging area (8 warps x 8 KiB)
+    if (pipe_bytes < 72 * 1024) pipe_bytes = 72 * 1024;            // room for the epilogue staging area (8 warps x 8 KiB) + channel sums
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
     uint64_t* empty = full + g.stages;
     uint64_t* accum_ready = empty + g.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_ready + 1);
     float* bias_s = reinterpret_cast<float*>(smem + pipe_bytes + 256);   // [8 warps][256]
+    // [4 lane quarters][2][256] channel sums (stats mode): lives in the idle pipeline area right after the 64 KiB of
+    // epilogue staging; every slot that is read is written exactly once, so it needs no zeroing
+    float* stat_s = reinterpret_cast<float*>(smem + 64 * 1024);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -310,6 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
                 const bool col_ok = col < e.n_valid, full = col + 4 <= e.n_valid;
                 const float relu_lo = e.relu ? 0.0f : -INFINITY;
+                float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
                 if (col_ok) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -330,7 +334,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k], full, relu_lo);
+                    if constexpr (MODE == EPI_F16) {
+                        if (e.stats != nullptr) {            // instance-norm statistics of the conv output (bias included)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (val[k]) {
+                                    const float w[4] = {v[k].x + bb.x, v[k].y + bb.y, v[k].z + bb.z, v[k].w + bb.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) { s4[j] += w[j]; q4[j] += w[j] * w[j]; }
+                                }
+                        }
+                    }
                 }
+                }
+                if constexpr (MODE == EPI_F16) {
+                    if (e.stats != nullptr) {
+                        // deterministic: fixed-order shuffle over the 4 lanes that share these columns, one smem slot per
+                        // (lane quarter, column) written exactly once, quarters summed in order at the end of the CTA
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], 8);
+                            s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], 16);
+                            q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], 8);
+                            q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], 16);
+                        }
+                        if (sub == 0) {
+                            float* dst = stat_s + q * 512 + c * 32 + cq * 4;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { dst[j] = s4[j]; dst[256 + j] = q4[j]; }
+                        }
+                    }
                 }
                 if (tt) tstamp[11 + (c >> 1) * 4] = clock64();
             }
@@ -341,6 +374,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     // no CTA may exit while a peer can still multicast into its smem / arrive on its barriers
     if (g.cluster > 1) cluster_sync_all(); else __syncthreads();
+    if (e.stats != nullptr) {
+        const int cg = ny * g.n_tile + threadIdx.x;
+        if (threadIdx.x < g.n_tile && cg < e.n_valid) {
+            const float* p0 = stat_s + threadIdx.x;
+            const float sum = ((p0[0] + p0[512]) + p0[1024]) + p0[1536];
+            const float sq = ((p0[256] + p0[768]) + p0[1280]) + p0[1792];
+            atomicAdd(e.stats + cg, static_cast<double>(sum));
+            atomicAdd(e.stats + e.n_valid + cg, static_cast<double>(sq));
+        }
+    }
     if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
     if (tstamp && threadIdx.x == 0) tstamp[6] = clock64();
 }
@@ -803,7 +846,7 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
         if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     } else {
         size_t pipe = static_cast<size_t>(g.stages) * (kTileM * 128 + g.n_tile * 128);
-        if (pipe < 64 * 1024) pipe = 64 * 1024;                    // the epilogue stages 8 warps x 2 x 4 KiB in the idle pipeline slots
+        if (pipe < 72 * 1024) pipe = 72 * 1024;                    // the epilogue stages 8 warps x 2 x 4 KiB (+ 8 KiB channel sums) in the idle pipeline slots
         const size_t smem = pipe + 256 /* barriers + TMEM slot */ + 8 * 256 * sizeof(float) /* bias copies */ + 1024;
         static bool attr_set = false;
         if (!attr_set) {

@@ -197,12 +197,15 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb2
     const int P2 = H2 * W2;
     const TapList t1 = taps_rect(1, 1), t3 = taps_rect(3, 3);
 
-    // raw -> instance norm (+relu) (+residual) -> out
+    // raw -> instance norm (+relu) (+residual) -> out.  The statistics were accumulated by the conv that produced
+    // `raw` (ConvEpi::stats, site-th block of c->sums; all blocks are zeroed once per frame).
+    int site = 0;
     auto norm = [&](__half* raw, int P, int C, int relu, const __half* res, __half* out) {
+        const int st = site++;
+        B.epi(static_cast<int>(c->plans.size()) - 1).stats = c->sums + st * 256;
         S.push_back([=](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-            launch_instnorm_stats(raw, 1, P, C, cc->sums, s);
-            launch_instnorm_apply(raw, cc->sums, 1, P, C, relu, res, out, s);
-            cc->launches += 2;
+            launch_instnorm_apply(raw, cc->sums + st * 256, 1, P, C, relu, res, out, s);
+            cc->launches += 1;
             return nullptr;
         });
     };
@@ -530,7 +533,7 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     for (int i = 0; i < 4; ++i) chk(c->E2[i] = c->dalloc<__half>(P2 * 64));
     chk(c->raw = c->dalloc<__half>(P2 * 64));
     chk(c->raw2 = c->dalloc<__half>(P2 * 64));
-    chk(c->sums = c->dalloc<double>(2 * 256));
+    chk(c->sums = c->dalloc<double>(16 * 2 * 128));      // one [2][C] block per instance-norm site of fnet
     chk(c->fmap_slots = c->dalloc<__half>(npx * 256 * n_slots));
     chk(c->net_slots = c->dalloc<float>(npx * 128 * n_slots));
     chk(c->inp_slots = c->dalloc<__half>(npx * 128 * n_slots));
@@ -565,6 +568,7 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     Builder B{c};
     c->plans.reserve(128);
     c->enc_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+        cudaMemsetAsync(cc->sums, 0, sizeof(double) * 16 * 2 * 128, s);
         launch_frame_patches(cc->frame_u8, cc->H, cc->W, cc->Hp, cc->Wp, cc->pad_l, cc->pad_t, cc->patches, s);
         cc->launches++;
         return nullptr;
