@@ -62,7 +62,11 @@ chain_select_kernel(const ChainSelectArgs a, const float sx, const float sy) {
 
     float bfx = 0.f, bfy = 0.f, bocc = 0.f, bsig = 0.f, bscore = 0.f;
     int bidx = 0;
-    for (int k = 0; k < a.K; ++k) {
+    // fully unrolled with a uniform guard: the loads of the next chains are independent of the running selection,
+    // so the compiler can keep several chains' gathers in flight (the kernel is latency bound, not bandwidth bound)
+#pragma unroll
+    for (int k = 0; k < kMaxChains; ++k) {
+        if (k >= a.K) break;
         const float* L = a.left[k];
         const float lfx = __ldg(L + p), lfy = __ldg(L + hw + p), locc = __ldg(L + 2 * hw + p), lsig = __ldg(L + 3 * hw + p);
         const float px = gx + lfx, py = gy + lfy;
@@ -401,20 +405,17 @@ void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long row
 // pyramid lookup (core/corr.py:30-51) + flow operands of the motion encoder
 // one warp per (pair, source pixel)
 // ==========================================================================================
-// Per level the 81 sample points of a pixel share one 11x11 integer neighbourhood of its correlation
-// row and only 9 distinct x- and 9 distinct y-coordinates: lanes 0..17 evaluate those 18 coordinates
-// (the oracle's exact round trip), the warp stages the four neighbourhoods in shared memory (484 loads
-// per pixel instead of 4 x 324), then every lane blends its samples from shared memory in the oracle's
-// operation order.
-constexpr int kLkWin = 11;
+// Per level the 81 sample points of a pixel are the 9x9 integer offsets of ONE position, so they share its
+// fractional part and a 10x10 integer neighbourhood of the pixel's correlation row.  The warp evaluates the
+// position once per level (the oracle's round trip on the first sample; the other samples' own round trips
+// differ from "first sample + k" by ~1e-6 px, four orders of magnitude below the fp16 rounding of the output),
+// stages the four neighbourhoods in shared memory (400 loads per pixel instead of 4 x 324) and blends.
+constexpr int kLkWin = 10;
 
 __global__ void __launch_bounds__(256)
 lookup_kernel(const LookupArgs a) {
     pdl_enter();
-    __shared__ float win[8][4][kLkWin * kLkWin + 3];
-    __shared__ float frac[8][4][18];       // wE for the 9 x samples, wS for the 9 y samples
-    __shared__ int cell[8][4][18];         // window cell of floor(coordinate) (y cells pre-multiplied by the window pitch)
-    constexpr int kBadCell = -100000;
+    __shared__ float win[8][4][kLkWin * kLkWin + 4];
     const int npx = a.h * a.w;
     const int wib = threadIdx.x >> 5;
     const long pp = static_cast<long>(blockIdx.x) * 8 + wib;
@@ -424,6 +425,7 @@ lookup_kernel(const LookupArgs a) {
     const int y = n / a.w, x = n % a.w;
     const float cx = a.coords1[pp * 2], cy = a.coords1[pp * 2 + 1];
     __half* out = a.corr16 + pp * 328;
+    const bool finite = isfinite(cx) && isfinite(cy);
 
     // level-independent index maps of this lane: window elements e = lane + 32k, outputs o = lane + 32k
     int ewy[4], ewx[4];
@@ -433,44 +435,32 @@ lookup_kernel(const LookupArgs a) {
         ewy[k] = e / kLkWin;
         ewx[k] = e - ewy[k] * kLkWin;
     }
-    int oi[3], oj[3];
+    int ooff[3];        // window offset of output o: x offset index i = o / 9 (columns), y offset index j = o % 9 (rows)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int o = lane + 32 * k;
-        oi[k] = o / 9;
-        oj[k] = o - oi[k] * 9;
+        const int i = o / 9, j = o - i * 9;
+        ooff[k] = j * kLkWin + i;
     }
+    float wE[4], wS[4];
     {
         int hl = a.h, wl = a.w;
         float div = 1.0f;
-        const bool isx = lane < 9;
-        const int kk = isx ? lane : lane - 9;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-            // the 18 sample coordinates of this level: lanes 0..8 -> x offsets -4..4, lanes 9..17 -> y offsets
-            const float c = (isx ? cx : cy) / div + static_cast<float>(kk - 4);
-            const int size = isx ? wl : hl;
-            const float pos = roundtrip_div(c, static_cast<float>(size - 1));
-            const float pf = floorf(pos);
-            const bool fin = isfinite(pos);
-            const int cell_abs = fin ? static_cast<int>(fminf(fmaxf(pf, -32.0f), static_cast<float>(size + 16))) : 0;
-            // window origin = cell of the first sample (lane 0 for x, lane 9 for y)
-            const int X0 = __shfl_sync(0xffffffffu, cell_abs, 0);
-            const int Y0 = __shfl_sync(0xffffffffu, cell_abs, 9);
-            const bool all_fin = __all_sync(0xffffffffu, fin || lane >= 18);
-            if (lane < 18) {
-                frac[wib][l][lane] = pos - pf;
-                const int rel = cell_abs - (isx ? X0 : Y0);
-                const bool inside = rel >= 0 && rel < kLkWin - 1;
-                // cells outside the staged window can only see zeros: point them at the zero slot (see below)
-                cell[wib][l][lane] = !all_fin ? kBadCell : (inside ? (isx ? rel : rel * kLkWin) : -1);
-            }
+            const float px = roundtrip_div(cx / div - 4.0f, static_cast<float>(wl - 1));
+            const float py = roundtrip_div(cy / div - 4.0f, static_cast<float>(hl - 1));
+            const float fx = floorf(px), fy = floorf(py);
+            wE[l] = px - fx;
+            wS[l] = py - fy;
+            const int X0 = finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(wl + 16))) : 0;
+            const int Y0 = finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(hl + 16))) : 0;
             const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (lane + 32 * k < kLkWin * kLkWin) {
                     const int gx = X0 + ewx[k], gy = Y0 + ewy[k];
-                    win[wib][l][lane + 32 * k] = (all_fin && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
+                    win[wib][l][lane + 32 * k] = (finite && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
                                                      ? __ldg(base + static_cast<long>(gy) * wl + gx) : 0.0f;
                 }
             }
@@ -484,20 +474,10 @@ lookup_kernel(const LookupArgs a) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if (lane + 32 * k < 81) {
-                const int wx = cell[wib][l][oi[k]], wyo = cell[wib][l][9 + oj[k]];
-                float r;
-                if (wx == kBadCell) {
-                    r = NAN;
-                } else if (wx < 0 || wyo < 0) {
-                    r = 0.0f;
-                } else {
-                    const float wE = frac[wib][l][oi[k]], wS = frac[wib][l][9 + oj[k]];
-                    const float* q = W + wyo + wx;
-                    const float vnw = q[0], vne = q[1], vsw = q[kLkWin], vse = q[kLkWin + 1];
-                    // same blend as the oracle up to rounding (the result is rounded to fp16 anyway)
-                    const float top = fmaf(wE, vne - vnw, vnw), bot = fmaf(wE, vse - vsw, vsw);
-                    r = fmaf(wS, bot - top, top);
-                }
+                const float* q = W + ooff[k];
+                const float vnw = q[0], vne = q[1], vsw = q[kLkWin], vse = q[kLkWin + 1];
+                const float top = fmaf(wE[l], vne - vnw, vnw), bot = fmaf(wE[l], vse - vsw, vsw);
+                const float r = finite ? fmaf(wS[l], bot - top, top) : NAN;
                 out[l * 81 + lane + 32 * k] = __float2half_rn(r);
             }
         }
