@@ -31,6 +31,7 @@ constexpr int kChunkK = 64;       // fp16 channels per pipeline stage (= one 128
 struct ConvGeom {
     int H, W;                     // OUTPUT height / width
     int nbatch;                   // batch entries covered by this launch
+    int b0;                       // first batch entry of this launch (sub-batches of the pair batch run as separate launches)
     int tile_h, tile_w;           // tile_h * tile_w == 128, tile_w a power of two
     int tile_w_log2;
     int tiles_x, tiles_y;
@@ -102,6 +103,6 @@ void conv_set_pdl(int on);
 void conv_set_smem_cap_kib(int kib);
 
 // Launch on `stream`; nbatch <= batch given at init.  use_simt=1 runs the SIMT cross-check kernel.
-const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt);
+const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt, int b0 = 0);
 
 }  // namespace mftb

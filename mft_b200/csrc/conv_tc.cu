@@ -173,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tx = t % g.tiles_x;
     t /= g.tiles_x;
     const int ty = t % g.tiles_y;
-    const int b = t / g.tiles_y;
+    const int b = g.b0 + t / g.tiles_y;
     const int ny = blockIdx.y;
 
     if (threadIdx.x == 0) {
@@ -292,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 8; ++k) {
                 const int row = q * 32 + k * 4 + sub;
                 const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & tw_mask);
-                if (y < g.H && x < g.W && b < g.nbatch) valid_bits |= 1u << k;
+                if (y < g.H && x < g.W && b < g.b0 + g.nbatch) valid_bits |= 1u << k;
                 pixr[k] = (static_cast<long>(b) * g.H + y) * g.W + x;
             }
             for (int c = cpar; c < nchunk; c += 2) {
@@ -430,7 +430,7 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tx = t % g.tiles_x;
     t /= g.tiles_x;
     const int ty = t % g.tiles_y;
-    const int b = t / g.tiles_y;
+    const int b = g.b0 + t / g.tiles_y;
     const int ny = blockIdx.y;
 
     if (threadIdx.x == 0) {
@@ -532,7 +532,7 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int k = 0; k < 8; ++k) {
                 const int m = q * 32 + k * 4 + sub;
                 const int y = ty * 16 + (m >> 3), x = tx * 16 + (m & 7);
-                if (y < g.H && b < g.nbatch) {
+                if (y < g.H && b < g.b0 + g.nbatch) {
                     if (x < g.W) valid_bits |= 1u << k;
                     if (x + 8 < g.W) valid_bits |= 1u << (8 + k);
                 }
@@ -600,7 +600,7 @@ conv_simt_kernel(const __half* __restrict__ A, int a_pitch, int a_cin, int in_H,
     const int tx = t % g.tiles_x;
     t /= g.tiles_x;
     const int ty = t % g.tiles_y;
-    const int b = t / g.tiles_y;
+    const int b = g.b0 + t / g.tiles_y;
     const int ny = blockIdx.y;
     const int row = threadIdx.x;
     const int yy = row / g.tile_w, xx = row - yy * g.tile_w;
@@ -813,9 +813,10 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
 }
 
 template <int MODE>
-static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt) {
+static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt, int b0) {
     ConvGeom g = p.g;
     g.nbatch = nbatch;
+    g.b0 = b0;
     dim3 grid(static_cast<unsigned>(g.tiles_x * g.tiles_y * nbatch), static_cast<unsigned>(g.n_tiles));
     if (use_simt) {
         conv_simt_kernel<MODE><<<grid, 128, 0, stream>>>(p.a_base, p.a_pitch, p.a_cin, p.in_H, p.in_W, p.b_base,
@@ -823,6 +824,7 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
     } else if (p.variant == 2) {
         ConvGeom g2 = p.g2;
         g2.nbatch = nbatch;
+        g2.b0 = b0;
         size_t pipe = static_cast<size_t>(g2.na) * g2.pxp * g2.py * 128 + static_cast<size_t>(g2.nb) * g2.n_tile * 128;
         if (pipe < 64 * 1024) pipe = 64 * 1024;
         const size_t smem = pipe + 256 + 8 * 256 * sizeof(float) + 1024;
@@ -883,14 +885,14 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }
 
-const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt) {
+const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt, int b0) {
     switch (p.mode) {
-        case EPI_F16: return launch_mode<EPI_F16>(p, nbatch, stream, use_simt);
-        case EPI_F32: return launch_mode<EPI_F32>(p, nbatch, stream, use_simt);
-        case EPI_CNET: return launch_mode<EPI_CNET>(p, nbatch, stream, use_simt);
-        case EPI_GRU_ZR: return launch_mode<EPI_GRU_ZR>(p, nbatch, stream, use_simt);
-        case EPI_GRU_Q: return launch_mode<EPI_GRU_Q>(p, nbatch, stream, use_simt);
-        case EPI_FLOW: return launch_mode<EPI_FLOW>(p, nbatch, stream, use_simt);
+        case EPI_F16: return launch_mode<EPI_F16>(p, nbatch, stream, use_simt, b0);
+        case EPI_F32: return launch_mode<EPI_F32>(p, nbatch, stream, use_simt, b0);
+        case EPI_CNET: return launch_mode<EPI_CNET>(p, nbatch, stream, use_simt, b0);
+        case EPI_GRU_ZR: return launch_mode<EPI_GRU_ZR>(p, nbatch, stream, use_simt, b0);
+        case EPI_GRU_Q: return launch_mode<EPI_GRU_Q>(p, nbatch, stream, use_simt, b0);
+        case EPI_FLOW: return launch_mode<EPI_FLOW>(p, nbatch, stream, use_simt, b0);
     }
     return "conv_launch: unknown epilogue mode";
 }

@@ -86,14 +86,20 @@ struct mftb200_ctx {
         Step(F f, int k = 1) : fn(std::move(f)), kind(k) {}
     };
     std::vector<Step> enc_steps, pre_steps, iter_steps, final_steps;
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // streams: group g of the pair batch runs on gs[g][0] (+ gs[g][1] for its independent branch).  gs[0][0] is the
+    // caller's stream of the current call; the other three belong to the engine.
+    cudaStream_t gs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr}, ev_start = nullptr, ev_done = nullptr;
+    int cur_group = 0, cur_b0 = 0;
+    // run the pair batch as two concurrent half-batches; measured slower at 512^2 (204 vs 225 frames/s: twice the launches,
+    // each with its own prologue / epilogue tail), so off by default -- kept as a tuning option, results are bit-identical
+    int split_pairs = 0;
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
     std::vector<cudaEvent_t> prof_events;   // pairs
     std::vector<int> prof_kinds, prof_tags;
-    int cur_slot = 0, cur_pairs = 0;
+    int cur_slot = 0, cur_pairs = 0;       // cur_pairs / cur_b0: size and first pair of the sub-batch being enqueued
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -180,7 +186,7 @@ mftb200_ctx::Step sync_step(int kind) {
 mftb200_ctx::Step conv_step(int plan_idx, bool batched_pairs) {
     return mftb200_ctx::Step([plan_idx, batched_pairs](mftb200_ctx* c, cudaStream_t s) -> const char* {
         c->launches++;
-        return conv_launch(c->plans[plan_idx], batched_pairs ? c->cur_pairs : 1, s, c->conv_impl);
+        return conv_launch(c->plans[plan_idx], batched_pairs ? c->cur_pairs : 1, s, c->conv_impl, batched_pairs ? c->cur_b0 : 0);
     }, 0);
 }
 
@@ -287,8 +293,9 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
 
     // ---- once per call: gather features, build correlation pyramid -------------------------
     c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-        PairSetup a{cc->slot_table, cc->fmap_slots, cc->net_slots, cc->inp_slots, cc->F1, cc->F2, cc->h32, cc->X,
-                    cc->coords1, cc->cur_pairs, cc->h, cc->w};
+        const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;        // first pixel row of this sub-batch
+        PairSetup a{cc->slot_table + 2 * cc->cur_b0, cc->fmap_slots, cc->net_slots, cc->inp_slots, cc->F1 + o * 256,
+                    cc->F2 + o * 256, cc->h32 + o * 128, cc->X + o * 512, cc->coords1 + o * 2, cc->cur_pairs, cc->h, cc->w};
         launch_pair_setup(a, s);
         cc->launches++;
         return nullptr;
@@ -303,8 +310,11 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         c->pre_steps.push_back(B.step(i, true));
     }
     c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-        launch_corr_pool(cc->corr[0], cc->corr[1], cc->corr[2], cc->corr[3], static_cast<long>(cc->cur_pairs) * cc->npx,
-                         cc->h, cc->w, s);
+        const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
+        const size_t n0 = static_cast<size_t>(cc->h) * cc->w, n1 = static_cast<size_t>(cc->h / 2) * (cc->w / 2),
+                     n2 = static_cast<size_t>(cc->h / 4) * (cc->w / 4), n3 = static_cast<size_t>(cc->h / 8) * (cc->w / 8);
+        launch_corr_pool(cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3,
+                         static_cast<long>(cc->cur_pairs) * cc->npx, cc->h, cc->w, s);
         cc->launches++;
         return nullptr;
     });
@@ -312,8 +322,12 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     // ---- one GRU iteration (core/raft.py:173-184, core/update.py:229-238) ------------------
     auto& S = c->iter_steps;
     S.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-        LookupArgs a{{cc->corr[0], cc->corr[1], cc->corr[2], cc->corr[3]}, cc->coords1, cc->corr16, cc->flowpatch,
-                     cc->X, cc->cur_pairs, cc->h, cc->w};
+        const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
+        const size_t n0 = static_cast<size_t>(cc->h) * cc->w, n1 = static_cast<size_t>(cc->h / 2) * (cc->w / 2),
+                     n2 = static_cast<size_t>(cc->h / 4) * (cc->w / 4), n3 = static_cast<size_t>(cc->h / 8) * (cc->w / 8);
+        LookupArgs a{{cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3},
+                     cc->coords1 + o * 2, cc->corr16 + o * 328, cc->flowpatch + o * 104, cc->X + o * 512, cc->cur_pairs,
+                     cc->h, cc->w};
         launch_lookup(a, s);
         cc->launches++;
         return nullptr;
@@ -377,7 +391,9 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         Fz.push_back(B.step(i, true));
     }
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-        OuPackArgs a{cc->X, cc->corr16, cc->coords1, cc->delta32, cc->oupack, cc->cur_pairs, cc->h, cc->w};
+        const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
+        OuPackArgs a{cc->X + o * 512, cc->corr16 + o * 328, cc->coords1 + o * 2, cc->delta32 + o * 2, cc->oupack + o * 720,
+                     cc->cur_pairs, cc->h, cc->w};
         launch_ou_pack(a, s);
         cc->launches++;
         return nullptr;
@@ -393,7 +409,9 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         Fz.push_back(B.step(i, true));
     }
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-        UpsampleArgs a{cc->mask32, cc->coords1, cc->ou32, cc->out, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
+        const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
+        UpsampleArgs a{cc->mask32 + o * 576, cc->coords1 + o * 2, cc->ou32 + o * 4,
+                       cc->out + static_cast<size_t>(cc->cur_b0) * 4 * cc->H * cc->W, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
                        cc->pad_l, cc->pad_t};
         launch_upsample(a, s);
         cc->launches++;
@@ -402,34 +420,60 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     return B.err;
 }
 
+// Enqueues one step on the streams of the current group (c->cur_group).
+int run_one(mftb200_ctx* c, mftb200_ctx::Step& st) {
+    cudaStream_t main_stream = c->gs[c->cur_group][0], side = c->gs[c->cur_group][1];
+    if (c->profile && st.sync != 0) return MFTB200_OK;      // profiling serialises everything on the caller's stream
+    if (st.sync == 1) {            // fork: the side stream may start once everything queued so far is done
+        cudaEventRecord(c->ev_fork[c->cur_group], main_stream);
+        cudaStreamWaitEvent(side, c->ev_fork[c->cur_group], 0);
+        return MFTB200_OK;
+    }
+    if (st.sync == 2) {            // join
+        cudaEventRecord(c->ev_join[c->cur_group], side);
+        cudaStreamWaitEvent(main_stream, c->ev_join[c->cur_group], 0);
+        return MFTB200_OK;
+    }
+    cudaStream_t s = (st.lane && !c->profile) ? side : main_stream;
+    if (c->profile) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+        const char* e = st.fn(c, s);
+        cudaEventRecord(b, s);
+        c->prof_events.push_back(a);
+        c->prof_events.push_back(b);
+        c->prof_kinds.push_back(st.kind);
+        c->prof_tags.push_back(st.tag);
+        if (e) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+    } else if (const char* e = st.fn(c, s)) {
+        return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+    }
+    return MFTB200_OK;
+}
+
 int run_steps(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cudaStream_t main_stream) {
+    c->gs[0][0] = main_stream;
+    c->cur_group = 0;
+    c->cur_b0 = 0;
     for (auto& st : steps) {
-        if (c->profile && st.sync != 0) continue;      // profiling serialises everything on the caller's stream
-        if (st.sync == 1) {            // fork: the side stream may start once everything queued so far is done
-            cudaEventRecord(c->ev_fork, main_stream);
-            cudaStreamWaitEvent(c->side, c->ev_fork, 0);
-            continue;
-        }
-        if (st.sync == 2) {            // join
-            cudaEventRecord(c->ev_join, c->side);
-            cudaStreamWaitEvent(main_stream, c->ev_join, 0);
-            continue;
-        }
-        cudaStream_t s = (st.lane && !c->profile) ? c->side : main_stream;
-        if (c->profile) {
-            cudaEvent_t a, b;
-            cudaEventCreate(&a);
-            cudaEventCreate(&b);
-            cudaEventRecord(a, s);
-            const char* e = st.fn(c, s);
-            cudaEventRecord(b, s);
-            c->prof_events.push_back(a);
-            c->prof_events.push_back(b);
-            c->prof_kinds.push_back(st.kind);
-            c->prof_tags.push_back(st.tag);
-            if (e) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
-        } else if (const char* e = st.fn(c, s)) {
-            return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+        const int r = run_one(c, st);
+        if (r != MFTB200_OK) return r;
+    }
+    return MFTB200_OK;
+}
+
+// The same steps for several sub-batches of the pair batch, interleaved step by step so every stream stays fed.
+struct Group { int b0, np; };
+int run_steps_groups(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, const Group* groups, int n_groups) {
+    for (auto& st : steps) {
+        for (int gi = 0; gi < n_groups; ++gi) {
+            c->cur_group = gi;
+            c->cur_b0 = groups[gi].b0;
+            c->cur_pairs = groups[gi].np;
+            const int r = run_one(c, st);
+            if (r != MFTB200_OK) return r;
         }
     }
     return MFTB200_OK;
@@ -466,9 +510,15 @@ int mftb200_create(mftb200_ctx** out) {
         return MFTB200_ERR_CUDA;
     }
     cudaMemset(c->err_flag, 0, 256);
-    cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->gs[0][1], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->gs[1][0], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->gs[1][1], cudaStreamNonBlocking);
+    for (int g = 0; g < 2; ++g) {
+        cudaEventCreateWithFlags(&c->ev_fork[g], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_join[g], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
     *out = c;
     return MFTB200_OK;
 }
@@ -481,9 +531,15 @@ void mftb200_destroy(mftb200_ctx* c) {
         cudaFree(L.bias);
     }
     cudaFree(c->err_flag);
-    if (c->side) cudaStreamDestroy(c->side);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->gs[0][1]) cudaStreamDestroy(c->gs[0][1]);
+    if (c->gs[1][0]) cudaStreamDestroy(c->gs[1][0]);
+    if (c->gs[1][1]) cudaStreamDestroy(c->gs[1][1]);
+    for (int g = 0; g < 2; ++g) {
+        if (c->ev_fork[g]) cudaEventDestroy(c->ev_fork[g]);
+        if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
 }
 
@@ -628,10 +684,31 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
     // pageable source: the runtime stages the copy before returning, so `table` may go out of scope
     if (cudaMemcpyAsync(c->slot_table, table, sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, s) != cudaSuccess)
         return c->fail(MFTB200_ERR_CUDA, "raft_refine: slot table copy failed");
+    // Two concurrent half-batches: each half's convs fit in one wave of CTAs, and the two dependency chains fill each
+    // other's idle SMs at layer boundaries (a single 7-pair batch leaves 72 of 148 SMs idle for half of every conv).
+    Group groups[2] = {{0, n_pairs}, {0, 0}};
+    int n_groups = 1;
+    if (c->split_pairs && !c->profile && n_pairs >= 4) {
+        groups[0].np = (n_pairs + 1) / 2;
+        groups[1].b0 = groups[0].np;
+        groups[1].np = n_pairs - groups[0].np;
+        n_groups = 2;
+    }
+    c->gs[0][0] = s;
+    if (n_groups == 2) {
+        cudaEventRecord(c->ev_start, s);
+        cudaStreamWaitEvent(c->gs[1][0], c->ev_start, 0);
+    }
+    int r = run_steps_groups(c, c->pre_steps, groups, n_groups);
+    for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) r = run_steps_groups(c, c->iter_steps, groups, n_groups);
+    if (r == MFTB200_OK) r = run_steps_groups(c, c->final_steps, groups, n_groups);
+    if (n_groups == 2) {
+        cudaEventRecord(c->ev_done, c->gs[1][0]);
+        cudaStreamWaitEvent(s, c->ev_done, 0);
+    }
+    c->cur_group = 0;
+    c->cur_b0 = 0;
     c->cur_pairs = n_pairs;
-    int r = run_steps(c, c->pre_steps, s);
-    for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) r = run_steps(c, c->iter_steps, s);
-    if (r == MFTB200_OK) r = run_steps(c, c->final_steps, s);
     if (r != MFTB200_OK) return r;
     if (cudaMemcpyAsync(out, c->out, sizeof(float) * 4 * n_pairs * c->H * c->W, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
         return c->fail(MFTB200_ERR_CUDA, "raft_refine: output copy failed");
@@ -684,6 +761,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (!c || !key) return MFTB200_ERR_ARG;
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
+    if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }

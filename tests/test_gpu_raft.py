@@ -143,6 +143,21 @@ def test_batched_equals_single_pair(seeded_weights):
         assert torch.equal(single[0], batch[p]), p
 
 
+def test_split_half_batches_bit_identical(seeded_weights):
+    """Engine option split_pairs (two concurrent half-batches on separate streams) must not change a single bit."""
+    from mft_b200.synth import synthetic_video
+    frames = list(synthetic_video(6, 128, 160, seed=4))
+    eng = _engine(seeded_weights, 128, 160, pairs=5, slots=6)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    ref = eng.refine([0, 1, 2, 3, 4], [5] * 5).clone()
+    eng.set_option('split_pairs', 1)
+    got = eng.refine([0, 1, 2, 3, 4], [5] * 5).clone()
+    eng.set_option('split_pairs', 0)
+    eng.check_device()
+    assert torch.equal(ref, got)
+
+
 def test_tracker_vs_oracle_real_128(real_weights):
     """mft_b200.MFT.MFT against the oracle tracker and the reference tracker's golden results."""
     from mft_b200.config import Config
