@@ -379,17 +379,11 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         S.push_back(B.step(i, true));
     }
 
-    // ---- after the last iteration: mask head, OU head, convex upsampling ---------------------
+    // ---- after the last iteration: mask head || OU head (independent until the upsampling), convex upsampling --------
     auto& Fz = c->final_steps;
+    Act a_ou1{c->c1buf, 256, 256, h, w};       // the OU branch keeps its hidden layer in c1buf (free after the last iteration)
+    Fz.push_back(sync_step(1));
     Fz.push_back(B.step(B.conv16(L_MASK1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
-    {
-        const int i = B.conv(L_MASK2, a_fh, mp, 1, t1, 192, EPI_F32);
-        if (i >= 0) {
-            ConvEpi& e = B.epi(i);
-            e.scale = 0.25f; e.out32 = c->mask32; e.out32_stride = 576; e.n_valid = 576;   // update.py:237
-        }
-        Fz.push_back(B.step(i, true));
-    }
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
         OuPackArgs a{cc->X + o * 512, cc->corr16 + o * 328, cc->coords1 + o * 2, cc->delta32 + o * 2, cc->oupack + o * 720,
@@ -398,16 +392,28 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         cc->launches++;
         return nullptr;
     });
-    Act a_ou{c->oupack, 720, 712, h, w};
-    Fz.push_back(B.step(B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    Fz.back().lane = 1;
     {
-        const int i = B.conv(L_OU2, a_fh, mp, 1, t3, 16, EPI_F32);
+        const int i = B.conv(L_MASK2, a_fh, mp, 1, t1, 192, EPI_F32);
+        if (i >= 0) {
+            ConvEpi& e = B.epi(i);
+            e.scale = 0.25f; e.out32 = c->mask32; e.out32_stride = 576; e.n_valid = 576;   // update.py:237
+        }
+        Fz.push_back(B.step(i, true));
+    }
+    Act a_ou{c->oupack, 720, 712, h, w};
+    Fz.push_back(B.step(B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->c1buf, 256, 0, 256), true));
+    Fz.back().lane = 1;
+    {
+        const int i = B.conv(L_OU2, a_ou1, mp, 1, t3, 16, EPI_F32);
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
             e.out32 = c->ou32; e.out32_stride = 4; e.n_valid = 3;
         }
         Fz.push_back(B.step(i, true));
+        Fz.back().lane = 1;
     }
+    Fz.push_back(sync_step(2));
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
         UpsampleArgs a{cc->mask32 + o * 576, cc->coords1 + o * 2, cc->ou32 + o * 4,

@@ -331,28 +331,36 @@ void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, 
 // per-pair state set-up (core/raft.py:141-154): gather cached per-frame features, net/inp split,
 // coords1 = coords0 = grid
 // ==========================================================================================
-__global__ void __launch_bounds__(128)
+// one warp per (pair, pixel): 16-byte vector copies of the cached per-frame features
+__global__ void __launch_bounds__(256)
 pair_setup_kernel(const PairSetup a) {
     pdl_enter();
     const int npx = a.h * a.w;
-    const long pp = blockIdx.x;                 // pair * npx + n
+    const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);      // pair * npx + n
+    if (pp >= static_cast<long>(a.n_pairs) * npx) return;
+    const int lane = threadIdx.x & 31;
     const int pair = static_cast<int>(pp / npx), n = static_cast<int>(pp % npx);
     const int ls = a.slots[2 * pair], rs = a.slots[2 * pair + 1];
-    const int t = threadIdx.x;                  // 128 threads
-    // fmaps: 256 halves = 128 half2 per pixel
-    reinterpret_cast<__half2*>(a.F1)[pp * 128 + t] =
-        reinterpret_cast<const __half2*>(a.fmap_slots)[(static_cast<long>(ls) * npx + n) * 128 + t];
-    reinterpret_cast<__half2*>(a.F2)[pp * 128 + t] =
-        reinterpret_cast<const __half2*>(a.fmap_slots)[(static_cast<long>(rs) * npx + n) * 128 + t];
-    const float hv = a.net_slots[(static_cast<long>(ls) * npx + n) * 128 + t];
-    a.h32[pp * 128 + t] = hv;
-    a.X[pp * 512 + t] = __float2half_rn(hv);
-    a.X[pp * 512 + 128 + t] = a.inp_slots[(static_cast<long>(ls) * npx + n) * 128 + t];
-    if (t < 2) a.coords1[pp * 2 + t] = static_cast<float>(t == 0 ? n % a.w : n / a.w);
+    const long lsrc = static_cast<long>(ls) * npx + n, rsrc = static_cast<long>(rs) * npx + n;
+    // fmaps: 256 halves = 32 x uint4 per pixel
+    reinterpret_cast<uint4*>(a.F1)[pp * 32 + lane] = reinterpret_cast<const uint4*>(a.fmap_slots)[lsrc * 32 + lane];
+    reinterpret_cast<uint4*>(a.F2)[pp * 32 + lane] = reinterpret_cast<const uint4*>(a.fmap_slots)[rsrc * 32 + lane];
+    // net: 128 floats = 32 x float4 -> fp32 master + fp16 operand copy (X[:, 0:128])
+    const float4 hv = reinterpret_cast<const float4*>(a.net_slots)[lsrc * 32 + lane];
+    reinterpret_cast<float4*>(a.h32)[pp * 32 + lane] = hv;
+    const __half2 h0 = __floats2half2_rn(hv.x, hv.y), h1 = __floats2half2_rn(hv.z, hv.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(a.X + pp * 512)[lane] = pk;
+    // inp: 128 halves = 16 x uint4 -> X[:, 128:256]
+    if (lane < 16) reinterpret_cast<uint4*>(a.X + pp * 512 + 128)[lane] = reinterpret_cast<const uint4*>(a.inp_slots)[lsrc * 16 + lane];
+    if (lane < 2) a.coords1[pp * 2 + lane] = static_cast<float>(lane == 0 ? n % a.w : n / a.w);
 }
 
 void launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
-    launch_pdl(pair_setup_kernel, dim3(static_cast<unsigned>(static_cast<long>(a.n_pairs) * a.h * a.w)), dim3(128), 0, stream, a);
+    const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
+    launch_pdl(pair_setup_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -511,6 +519,7 @@ void launch_lookup(const LookupArgs& a, cudaStream_t stream) {
 // ==========================================================================================
 // OU head input: [net | inp | corr | flow | delta_flow | motion] = 712 channels (update.py:197)
 // ==========================================================================================
+// 720 halves per pixel = 90 x 16 bytes: [X 0:256 | corr 0:320 | corr 320:324 + flow + delta | X 256:384 | zero pad]
 __global__ void __launch_bounds__(256)
 ou_pack_kernel(const OuPackArgs a) {
     pdl_enter();
@@ -519,17 +528,27 @@ ou_pack_kernel(const OuPackArgs a) {
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
     const int lane = threadIdx.x & 31;
     const int n = static_cast<int>(pp % npx);
-    const __half* X = a.X + pp * 512;
-    const __half* C = a.corr16 + pp * 328;
-    __half* o = a.packed + pp * 720;
-    for (int k = lane; k < 720; k += 32) {
-        __half v;
-        if (k < 256) v = X[k];
-        else if (k < 580) v = C[k - 256];
-        else if (k < 582) v = __float2half_rn(a.coords1[pp * 2 + (k - 580)] - static_cast<float>(k == 580 ? n % a.w : n / a.w));
-        else if (k < 584) v = __float2half_rn(a.delta32[pp * 2 + (k - 582)]);
-        else if (k < 712) v = X[256 + (k - 584)];
-        else v = __float2half_rn(0.0f);
+    const uint4* X = reinterpret_cast<const uint4*>(a.X + pp * 512);          // 64 chunks
+    const uint4* C = reinterpret_cast<const uint4*>(a.corr16 + pp * 328);     // 41 chunks (row pitch 656 B)
+    uint4* o = reinterpret_cast<uint4*>(a.packed + pp * 720);                  // 90 chunks
+    for (int k = lane; k < 90; k += 32) {
+        uint4 v;
+        if (k < 32) {
+            v = X[k];
+        } else if (k < 72) {
+            v = C[k - 32];
+        } else if (k == 72) {
+            const uint2 c4 = *reinterpret_cast<const uint2*>(a.corr16 + pp * 328 + 320);     // corr 320:324
+            const float fx = a.coords1[pp * 2] - static_cast<float>(n % a.w), fy = a.coords1[pp * 2 + 1] - static_cast<float>(n / a.w);
+            const __half2 f = __floats2half2_rn(fx, fy), d = __floats2half2_rn(a.delta32[pp * 2], a.delta32[pp * 2 + 1]);
+            v.x = c4.x; v.y = c4.y;
+            v.z = *reinterpret_cast<const uint32_t*>(&f);
+            v.w = *reinterpret_cast<const uint32_t*>(&d);
+        } else if (k < 89) {
+            v = X[32 + (k - 73)];
+        } else {
+            v = make_uint4(0u, 0u, 0u, 0u);
+        }
         o[k] = v;
     }
 }
