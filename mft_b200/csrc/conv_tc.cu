@@ -159,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // epilogue staging; every slot that is read is written exactly once, so it needs no zeroing
     float* stat_s = reinterpret_cast<float*>(smem + 64 * 1024);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform role index
     const int lane = threadIdx.x & 31;
     long long* tstamp = e.timing ? e.timing + (static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
     if (tstamp && threadIdx.x == 0) {
@@ -180,7 +180,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], 2);                                   // A producer + B producer
             mbar_init(&empty[s], static_cast<uint32_t>(g.cluster));   // one release per consumer CTA of the cluster
         }
         mbar_init(accum_ready, 1);
@@ -204,61 +204,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint16_t cmask = static_cast<uint16_t>((1u << g.cluster) - 1u);
     bool ok = true;
 
+    // Warp roles are warp-uniform (warp index via shuffle, loops run by all 32 lanes, the asynchronous instructions are
+    // issued by one elected lane): the compiler then keeps descriptors, coordinates and barrier addresses in uniform
+    // registers and emits UTMALDG / UTCHMMA / UTCBAR back to back.  Issuing them from a divergent `lane == 0` branch
+    // instead costs an ELECT / R2UR / branch "waterfall" per instruction: ~67 cycles per MMA for a single thread,
+    // which capped a CTA at one K=64 stage per ~600 cycles whatever N (tools/mma_probe.cu).
     if (warp == 0) {
-        if (lane == 0) {
-            const int x0 = g.stride * tx * g.tile_w;
-            const int y0 = g.stride * ty * g.tile_h;
-            const int brow = b * g.b_rows_per_batch + ny * g.n_tile;
-            int kc = 0, kx = 0, ky = 0, s = 0;
-            uint32_t ph = 0;
-            const int rx = g.kw / 2, ry = g.kh / 2;
-            for (int it = 0; it < T; ++it) {
-                if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
-                mbar_arrive_expect_tx(&full[s], stage_bytes);
-                uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
-                tma_load_4d(sa, &tmA, &full[s], kc * kChunkK, x0 + kx - rx, y0 + ky - ry, b);
+        // A-operand producer: one shifted activation box per (tap, 64-channel chunk)
+        const int x0 = g.stride * tx * g.tile_w;
+        const int y0 = g.stride * ty * g.tile_h;
+        int kc = 0, kx = 0, ky = 0, s = 0;
+        uint32_t ph = 0;
+        const int rx = g.kw / 2, ry = g.kh / 2;
+        for (int it = 0; it < T; ++it) {
+            if (!__all_sync(0xffffffffu, mbar_wait(&empty[s], ph ^ 1))) { ok = false; break; }
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&full[s], a_bytes);
+                tma_load_4d(smem + static_cast<size_t>(s) * stage_bytes, &tmA, &full[s], kc * kChunkK, x0 + kx - rx,
+                            y0 + ky - ry, b);
+            }
+            __syncwarp();
+            if (++kc == g.kchunks) {
+                kc = 0;
+                if (++kx == g.kw) { kx = 0; ++ky; }
+            }
+            if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 2) {
+        // B-operand producer (its own warp: the two box streams are issued independently)
+        const int brow = b * g.b_rows_per_batch + ny * g.n_tile;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < T; ++it) {
+            if (!__all_sync(0xffffffffu, mbar_wait(&empty[s], ph ^ 1))) { ok = false; break; }
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&full[s], b_bytes);
+                uint8_t* sb = smem + static_cast<size_t>(s) * stage_bytes + a_bytes;
                 if (g.cluster > 1) {
                     // each CTA fetches 1/cluster of the B slab and multicasts it to all CTAs of the cluster
                     const int slice = g.n_tile / g.cluster;
-                    tma_load_2d_mc(sa + a_bytes + crank * slice * 128, &tmB, &full[s], it * kChunkK,
+                    tma_load_2d_mc(sb + crank * slice * 128, &tmB, &full[s], it * kChunkK,
                                    brow + static_cast<int>(crank) * slice, cmask);
                 } else {
-                    tma_load_2d(sa + a_bytes, &tmB, &full[s], it * kChunkK, brow);
+                    tma_load_2d(sb, &tmB, &full[s], it * kChunkK, brow);
                 }
-                if (++kc == g.kchunks) {
-                    kc = 0;
-                    if (++kx == g.kw) { kx = 0; ++ky; }
-                }
-                if (++s == g.stages) { s = 0; ph ^= 1; }
             }
+            __syncwarp();
+            if (++s == g.stages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
-            // descriptors: constant high words, low word = (address >> 4) | LBO field; +2 per K=16 step (32 bytes)
-            const uint64_t d0 = umma_desc_k128(smem_u32(smem));
-            const uint32_t dhi = static_cast<uint32_t>(d0 >> 32);
-            uint32_t alo = static_cast<uint32_t>(d0);
-            const uint32_t alo0 = alo, stage_lo = stage_bytes >> 4, b_off_lo = a_bytes >> 4;
-            int s = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < T; ++it) {
-                if (!mbar_wait(&full[s], ph)) { ok = false; break; }
+        const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
+        // descriptors: constant high words, low word = (address >> 4) | LBO field; +2 per K=16 step (32 bytes)
+        const uint64_t d0 = umma_desc_k128(smem_u32(smem));
+        const uint32_t dhi = static_cast<uint32_t>(d0 >> 32);
+        uint32_t alo = static_cast<uint32_t>(d0);
+        const uint32_t alo0 = alo, stage_lo = stage_bytes >> 4, b_off_lo = a_bytes >> 4;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < T; ++it) {
+            if (!__all_sync(0xffffffffu, mbar_wait(&full[s], ph))) { ok = false; break; }
+            tc_fence_after();
+            if (elect_one()) {
                 if (tstamp && it == 0) tstamp[2] = clock64();
-                tc_fence_after();
                 const uint32_t blo = alo + b_off_lo;
-                // (Measured: one CTA sustains one MMA per ~147 cycles whatever N is, and dealing the K steps to several
-                //  independent TMEM accumulators does not change that -- narrow-N layers need co-resident CTAs.)
                 umma_f16_lohi(tmem_base, alo, dhi, blo, dhi, idesc, it != 0 ? 1u : 0u);
                 umma_f16_lohi(tmem_base, alo + 2, dhi, blo + 2, dhi, idesc, 1u);
                 umma_f16_lohi(tmem_base, alo + 4, dhi, blo + 4, dhi, idesc, 1u);
                 umma_f16_lohi(tmem_base, alo + 6, dhi, blo + 6, dhi, idesc, 1u);
                 // slot reusable once these MMAs have read it (in every CTA that multicasts into it)
                 if (g.cluster > 1) umma_commit_mc(&empty[s], cmask); else umma_commit(&empty[s]);
-                alo += stage_lo;
-                if (++s == g.stages) { s = 0; ph ^= 1; alo = alo0; }
             }
+            __syncwarp();
+            alo += stage_lo;
+            if (++s == g.stages) { s = 0; ph ^= 1; alo = alo0; }
+        }
+        if (elect_one()) {
             if (tstamp) tstamp[3] = clock64();
             umma_commit(accum_ready);     // accumulator complete
         }
