@@ -102,6 +102,50 @@ void conv_set_pdl(int on);
 // Caps the shared memory a CTA may use for pipeline stages (KiB, 0 = default 200).
 void conv_set_smem_cap_kib(int kib);
 
+// ------------------------------------------------------------------------------------------
+// Persistent layer program: several dependent convolutions of the SAME spatial geometry executed by ONE launch of
+// resident CTAs with tile-level dataflow between layers (conv_prog_kernel in conv_tc.cu).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxProgLayers = 12;
+
+struct ProgLayer {
+    CUtensorMap tmA, tmB;
+    ConvGeom g;
+    ConvEpi e;
+    int mode;
+    int dep0, dep1;               // program layers whose 3x3 tile neighbourhood (same batch entry) must be complete, -1 = none
+    int succ0, succ1;             // layers that list this one as a dependency (filled by conv_prog_add), -1 = none
+    int n_dep;                    // number of valid dependencies (0 = root layer: its tiles are ready at launch)
+    int pad_[2];
+};
+
+// Work distribution is a dataflow ready queue in global memory: a tile is pushed when the last of its predecessor
+// tiles completes (per-tile arrival counters), CTAs pop tickets in push order -- no CTA ever holds a tile that is not
+// ready to run.
+struct ConvProgram {
+    ProgLayer L[kMaxProgLayers];
+    int n_layers;
+    int nbatch, b0;               // batch entries covered by this launch
+    int max_batch;                // counter-array pitch
+    int tiles_x, tiles_y;         // common to every layer
+    unsigned epoch;               // tags the queue entries of THIS launch
+    unsigned long long head_base, tail_base;   // values of *head / *tail when this launch starts
+    unsigned long long* head;     // pop tickets (monotonic over launches)
+    unsigned long long* tail;     // push tickets
+    unsigned long long* queue;    // [queue_cap] entries (epoch << 32 | item), item = (layer * nbatch + batch) * tiles + tile
+    int queue_cap;
+    int* arrivals;                // [2][layer][max_batch][tiles_y*tiles_x]: set (epoch & 1) counts this launch, the other is cleared
+    int* err_flag;
+    long long* timing;            // optional [grid][16] per-CTA role timers (tuning aid)
+};
+
+// Appends plan `p` as the next layer of `prog` (checks the common geometry).  Returns nullptr or an error string.
+const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1);
+// One launch for the whole program; updates prog->epoch / counter_base for the next launch.
+const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, cudaStream_t stream);
+// Work items (= tile launches folded into the program) of a launch with `nbatch` batch entries.
+long conv_prog_items(const ConvProgram& prog, int nbatch);
+
 // Launch on `stream`; nbatch <= batch given at init.  use_simt=1 runs the SIMT cross-check kernel.
 const char* conv_launch(const ConvPlan& p, int nbatch, cudaStream_t stream, int use_simt, int b0 = 0);
 

@@ -6,7 +6,9 @@
 //   warps 2-5: epilogue (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> HBM)
 // Pipeline: `stages` smem slots guarded by full/empty mbarriers; accumulator hand-off through a
 // third mbarrier signalled by tcgen05.commit.
+#include <cstddef>
 #include <cstdio>
+#include <type_traits>
 #include <cstring>
 
 #include "conv.h"
@@ -33,27 +35,28 @@ struct EpiAux {
 
 // Pixel indices are 32-bit everywhere except the correlation volume (pixel * N^2 overflows): `pix` stays 64-bit in
 // the signature but every mode other than EPI_F32 does its address arithmetic on the low 32 bits (M * stride < 2^31).
-template <int MODE>
+// LEAN: the layer has neither a residual input nor fused statistics (checked by the host): compiled out.
+template <int MODE, bool LEAN = false>
 __device__ __forceinline__ EpiAux epi_prefetch(const ConvEpi& e, int col, long pix) {
     EpiAux x;
     x.a = make_float4(0.f, 0.f, 0.f, 0.f);
     x.b = x.a;
     const uint32_t p32 = static_cast<uint32_t>(pix);
     if constexpr (MODE == EPI_F16) {
-        if (e.res16 != nullptr && col + 4 <= e.n_valid) {
-            const uint2 rr = *reinterpret_cast<const uint2*>(e.res16 + (p32 * e.res_stride + e.res_coff + col));
+        if (!LEAN && e.res16 != nullptr && col + 4 <= e.n_valid) {
+            const uint2 rr = __ldcg(reinterpret_cast<const uint2*>(e.res16 + (p32 * e.res_stride + e.res_coff + col)));
             const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
             const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
             x.a = make_float4(r0.x, r0.y, r1.x, r1.y);
         }
     } else if constexpr (MODE == EPI_GRU_ZR) {
-        if (col >= 128) x.a = *reinterpret_cast<const float4*>(e.h32 + (p32 * 128u + (col - 128)));
+        if (col >= 128) x.a = __ldcg(reinterpret_cast<const float4*>(e.h32 + (p32 * 128u + (col - 128))));
     } else if constexpr (MODE == EPI_GRU_Q) {
-        x.a = *reinterpret_cast<const float4*>(e.h32 + (p32 * 128u + col));
-        x.b = *reinterpret_cast<const float4*>(e.z32 + (p32 * 128u + col));
+        x.a = __ldcg(reinterpret_cast<const float4*>(e.h32 + (p32 * 128u + col)));
+        x.b = __ldcg(reinterpret_cast<const float4*>(e.z32 + (p32 * 128u + col)));
     } else if constexpr (MODE == EPI_FLOW) {
         if (col == 0) {
-            const float2 c = *reinterpret_cast<const float2*>(e.coords1 + p32 * 2u);
+            const float2 c = __ldcg(reinterpret_cast<const float2*>(e.coords1 + p32 * 2u));
             x.a.x = c.x;
             x.a.y = c.y;
         }
@@ -70,7 +73,7 @@ __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) 
 }
 
 // `col` < n_valid is guaranteed by the caller; relu_lo = 0 (ReLU) or -inf (none) makes the activation branch-free.
-template <int MODE>
+template <int MODE, bool LEAN = false>
 __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const float4 bb, const EpiAux& ax, int col, long pix,
                                           bool full, float relu_lo) {
     v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -79,7 +82,7 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
         v.x = fmaxf(v.x, relu_lo); v.y = fmaxf(v.y, relu_lo); v.z = fmaxf(v.z, relu_lo); v.w = fmaxf(v.w, relu_lo);
         __half* o = e.out16 + (p32 * e.out16_stride + e.out16_coff + col);
         if (full) {
-            if (e.res16 != nullptr) {
+            if (!LEAN && e.res16 != nullptr) {
                 v.x = fmaxf(v.x + ax.a.x, 0.f); v.y = fmaxf(v.y + ax.a.y, 0.f);
                 v.z = fmaxf(v.z + ax.a.z, 0.f); v.w = fmaxf(v.w + ax.a.w, 0.f);
             }
@@ -88,7 +91,7 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
             const float a[4] = {v.x, v.y, v.z, v.w};
             for (int j = 0; j < 4 && col + j < e.n_valid; ++j) {
                 float x = a[j];
-                if (e.res16 != nullptr) x = fmaxf(x + __half2float(e.res16[p32 * e.res_stride + e.res_coff + col + j]), 0.f);
+                if (!LEAN && e.res16 != nullptr) x = fmaxf(x + __half2float(e.res16[p32 * e.res_stride + e.res_coff + col + j]), 0.f);
                 o[j] = __float2half_rn(x);
             }
         }
@@ -131,6 +134,124 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
             *reinterpret_cast<float2*>(e.delta32 + p32 * 2u) = make_float2(v.x, v.y);
             *reinterpret_cast<float2*>(e.coords1 + p32 * 2u) = make_float2(ax.a.x + v.x, ax.a.y + v.y);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue of one 128-pixel x n_tile accumulator tile, run by all 8 warps of the CTA
+// ------------------------------------------------------------------------------------------
+// Warp w reads TMEM lane quarter w%4 (hardware restriction) and the 32-column chunks of parity w/4, so each quarter is
+// drained by two warps.  The pipeline slots are idle by now (every TMA landed and every MMA read it): they are reused
+// as the per-warp staging area, 2 x [32 rows][32 fp32] with the 16-byte chunks XOR-swizzled by row.
+// STG = staging floats per warp: 2048 = double buffered, 1024 = single.  PRE: the epilogue's global inputs (GRU state,
+// residual) of a whole column chunk are requested BEFORE the accumulator chunk is pulled out of TMEM and staged, so their
+// L2 latency overlaps that work (the persistent kernel has the registers for it); bias then comes straight from global.
+template <int MODE, int STG = 2048, int PRE = 0, bool LEAN = false>      // PRE: 0 = off, 1 = bias from global only, 2 = bias + input prefetch
+__device__ __forceinline__ void tile_epilogue(const ConvGeom& g, const ConvEpi& e, uint8_t* smem, const float* bw,
+                                              float* stat_s, uint32_t tmem_base, int warp, int lane, int tx, int ty,
+                                              int b, int ny, long long* tstamp) {
+    const int q = warp & 3;
+    const int cpar = warp >> 2;
+    float* stg = reinterpret_cast<float*>(smem) + warp * STG;
+    const int sub = lane >> 3, cq = lane & 7;
+    const int tw_mask = g.tile_w - 1;
+    const int nchunk = (g.n_tile + 31) / 32;
+    // the 8 pixel rows this lane serves are the same for every column chunk (32-bit except for the correlation volume)
+    using PixT = typename std::conditional<MODE == EPI_F32, long, uint32_t>::type;
+    PixT pixr[8];
+    unsigned valid_bits = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int row = q * 32 + k * 4 + sub;
+        const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & tw_mask);
+        if (y < g.H && x < g.W && b < g.b0 + g.nbatch) valid_bits |= 1u << k;
+        pixr[k] = static_cast<PixT>((static_cast<PixT>(b) * g.H + y) * g.W + x);
+    }
+    for (int c = cpar; c < nchunk; c += 2) {
+        EpiAux axp[PRE == 2 ? 8 : 1];
+        if constexpr (PRE == 2) {
+            const int colp = ny * g.n_tile + c * 32 + cq * 4;
+            if (colp < e.n_valid) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((valid_bits >> k) & 1u) axp[k] = epi_prefetch<MODE, LEAN>(e, colp, pixr[k]);
+            }
+        }
+        uint32_t r[32];
+        const bool tt = tstamp && warp == 2 && lane == 0 && c < 4;
+        if (tt) tstamp[8 + (c >> 1) * 4] = clock64();
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        if (tt) tstamp[9 + (c >> 1) * 4] = clock64();
+        if constexpr (STG < 2048) __syncwarp();      // single staging buffer: everyone is done reading the previous chunk
+        float* buf = stg + (STG >= 2048 ? ((c >> 1) & 1) * 1024 : 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        if (tt) tstamp[10 + (c >> 1) * 4] = clock64();
+        const int col = ny * g.n_tile + c * 32 + cq * 4;
+        float4 bb;
+        if constexpr (PRE != 0) bb = e.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
+        const bool col_ok = col < e.n_valid, full = col + 4 <= e.n_valid;
+        const float relu_lo = e.relu ? 0.0f : -INFINITY;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (col_ok) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 v[4];
+            PixT pix[4];
+            bool val[4];
+            EpiAux ax[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rr = (half * 4 + k) * 4 + sub;
+                v[k] = *reinterpret_cast<const float4*>(buf + rr * 32 + ((cq ^ (rr & 7)) << 2));
+                val[k] = (valid_bits >> (half * 4 + k)) & 1u;
+                pix[k] = pixr[half * 4 + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if constexpr (PRE == 2) ax[k] = axp[half * 4 + k];
+                else if (val[k]) ax[k] = epi_prefetch<MODE, LEAN>(e, col, pix[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (val[k]) epilogue4<MODE, LEAN>(e, v[k], bb, ax[k], col, pix[k], full, relu_lo);
+            if constexpr (MODE == EPI_F16 && !LEAN) {
+                if (e.stats != nullptr) {            // instance-norm statistics of the conv output (bias included)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (val[k]) {
+                            const float w[4] = {v[k].x + bb.x, v[k].y + bb.y, v[k].z + bb.z, v[k].w + bb.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { s4[j] += w[j]; q4[j] += w[j] * w[j]; }
+                        }
+                }
+            }
+        }
+        }
+        if constexpr (MODE == EPI_F16 && !LEAN) {
+            if (e.stats != nullptr) {
+                // deterministic: fixed-order shuffle over the 4 lanes that share these columns, one smem slot per
+                // (lane quarter, column) written exactly once, quarters summed in order at the end of the CTA
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], 8);
+                    s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], 16);
+                    q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], 8);
+                    q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], 16);
+                }
+                if (sub == 0) {
+                    float* dst = stat_s + q * 512 + c * 32 + cq * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { dst[j] = s4[j]; dst[256 + j] = q4[j]; }
+                }
+            }
+        }
+        if (tt) tstamp[11 + (c >> 1) * 4] = clock64();
     }
 }
 
@@ -287,8 +408,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
         // ---- epilogue: all 8 warps.  Warp w reads TMEM lane quarter w%4 (hardware restriction) and the
         //      32-column chunks of parity w/4, so each quarter is drained by two warps.
-        const int q = warp & 3;
-        const int cpar = warp >> 2;
         // bias of this CTA's couts -> this warp's smem copy, while the main loop runs
         float* bw = bias_s + warp * 256;
         for (int i = lane; i < 256; i += 32)
@@ -298,96 +417,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ok = ok && ok_acc;
         if (tstamp && warp == 2 && lane == 0) tstamp[4] = clock64();
         tc_fence_after();
-        if (ok_acc) {
-            // The pipeline slots are idle now (every TMA landed and every MMA read it): reuse them as the
-            // per-warp staging area, 2 x [32 rows][32 fp32] with the 16-byte chunks XOR-swizzled by row.
-            float* stg = reinterpret_cast<float*>(smem) + warp * 2048;
-            const int sub = lane >> 3, cq = lane & 7;
-            const int tw_mask = g.tile_w - 1;
-            const int nchunk = (g.n_tile + 31) / 32;
-            // the 8 pixel rows this lane serves are the same for every column chunk
-            long pixr[8];
-            unsigned valid_bits = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int row = q * 32 + k * 4 + sub;
-                const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & tw_mask);
-                if (y < g.H && x < g.W && b < g.b0 + g.nbatch) valid_bits |= 1u << k;
-                pixr[k] = (static_cast<long>(b) * g.H + y) * g.W + x;
-            }
-            for (int c = cpar; c < nchunk; c += 2) {
-                uint32_t r[32];
-                const bool tt = tstamp && warp == 2 && lane == 0 && c < 4;
-                if (tt) tstamp[8 + (c >> 1) * 4] = clock64();
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
-                tmem_ld_wait();
-                if (tt) tstamp[9 + (c >> 1) * 4] = clock64();
-                float* buf = stg + ((c >> 1) & 1) * 1024;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                __syncwarp();
-                if (tt) tstamp[10 + (c >> 1) * 4] = clock64();
-                const int col = ny * g.n_tile + c * 32 + cq * 4;
-                const float4 bb = *reinterpret_cast<const float4*>(bw + c * 32 + cq * 4);
-                const bool col_ok = col < e.n_valid, full = col + 4 <= e.n_valid;
-                const float relu_lo = e.relu ? 0.0f : -INFINITY;
-                float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (col_ok) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 v[4];
-                    long pix[4];
-                    bool val[4];
-                    EpiAux ax[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int rr = (half * 4 + k) * 4 + sub;
-                        v[k] = *reinterpret_cast<const float4*>(buf + rr * 32 + ((cq ^ (rr & 7)) << 2));
-                        val[k] = (valid_bits >> (half * 4 + k)) & 1u;
-                        pix[k] = pixr[half * 4 + k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (val[k]) ax[k] = epi_prefetch<MODE>(e, col, pix[k]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (val[k]) epilogue4<MODE>(e, v[k], bb, ax[k], col, pix[k], full, relu_lo);
-                    if constexpr (MODE == EPI_F16) {
-                        if (e.stats != nullptr) {            // instance-norm statistics of the conv output (bias included)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (val[k]) {
-                                    const float w[4] = {v[k].x + bb.x, v[k].y + bb.y, v[k].z + bb.z, v[k].w + bb.w};
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) { s4[j] += w[j]; q4[j] += w[j] * w[j]; }
-                                }
-                        }
-                    }
-                }
-                }
-                if constexpr (MODE == EPI_F16) {
-                    if (e.stats != nullptr) {
-                        // deterministic: fixed-order shuffle over the 4 lanes that share these columns, one smem slot per
-                        // (lane quarter, column) written exactly once, quarters summed in order at the end of the CTA
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], 8);
-                            s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], 16);
-                            q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], 8);
-                            q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], 16);
-                        }
-                        if (sub == 0) {
-                            float* dst = stat_s + q * 512 + c * 32 + cq * 4;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { dst[j] = s4[j]; dst[256 + j] = q4[j]; }
-                        }
-                    }
-                }
-                if (tt) tstamp[11 + (c >> 1) * 4] = clock64();
-            }
-        }
+        if (ok_acc) tile_epilogue<MODE>(g, e, smem, bw, stat_s, tmem_base, warp, lane, tx, ty, b, ny, tstamp);
     }
     if (tstamp && warp == 2 && lane == 0) tstamp[5] = clock64();
     if (!ok && e.err_flag != nullptr) atomicExch(e.err_flag, 1 + warp);
@@ -406,6 +436,405 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(g.tmem_cols));
     if (tstamp && threadIdx.x == 0) tstamp[6] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent layer-program kernel: tile-level dataflow between dependent convolutions
+// ------------------------------------------------------------------------------------------
+// One launch runs a whole chain of convolutions (the 11 of a GRU iteration).  One resident CTA per SM pops work items
+// (layer, batch entry, tile) from a ready queue.  A tile of layer L becomes ready -- is pushed -- as soon as the 3x3
+// tile neighbourhood of its predecessor layer(s) is complete (per-tile arrival counters bumped with gpu-scope acq_rel
+// atomics + generic->async proxy fences, because the producer writes with st.global and the consumer reads with
+// TMA) -- not when the whole previous layer is.  Compared with one launch per layer this removes the per-launch drain /
+// fill bubbles (~7 us of every ~20 us launch at 512^2) and the 224-tiles-on-148-SMs wave quantisation: an SM that
+// is done with its share of layer L moves on to layer L+1.
+// A CTA only ever waits for a queue slot to be filled, i.e. for some running tile to complete, never for work that
+// has not been handed out, so the scheme cannot deadlock whatever the number of resident CTAs; every wait is bounded
+// and aborts the launch through err_flag instead of hanging.
+// The same 3x3 rule also covers the write-after-read hazards of the in-place GRU record (h and r*h slices of X are
+// overwritten by a later layer of the chain only after every tile that reads their halo is complete).
+// Shared-memory map (one CTA per SM, 384 threads):
+//   [0, 192K)     operand ring: 4 slots x 48 KiB (A box 16 KiB + B slab <= 32 KiB), the same slots for every layer
+//   [192K, 224K)  epilogue staging, 8 warps x 4 KiB
+//   [224K, 225K)  bias of the tile being drained
+//   [225K, 226K)  control block: mbarriers, TMEM base, ticket ring
+// Warp roles:  0 = A-operand producer   1 = MMA issuer   2 = B-operand producer   3 = scheduler (tickets + dependencies)
+//              4..11 = epilogue (warp w drains TMEM lane quarter w % 4, column chunks of parity (w - 4) / 4)
+// The last epilogue warp to finish a tile raises its completion flag.
+// Everything is decoupled by mbarriers, so that while the epilogue warps drain tile n from one TMEM accumulator the
+// MMA warp already accumulates tile n+1 into the other, the producers prefetch its operands and the scheduler waits
+// for the dependencies of tile n+2.
+constexpr int kProgThreads = 384;      // 12 warps = 3 per SM sub-partition: up to 168 registers per thread
+constexpr int kProgStages = 4;
+constexpr uint32_t kProgSlotBytes = 48 * 1024;
+constexpr uint32_t kProgStagingOff = kProgStages * kProgSlotBytes;
+constexpr uint32_t kProgBiasOff = kProgStagingOff + 8 * 4096;
+constexpr uint32_t kProgCtlOff = kProgBiasOff + 1024;
+constexpr uint32_t kProgSmemBytes = kProgCtlOff + 1024;
+constexpr int kProgTickets = 4;
+constexpr uint32_t kTicketEnd = 0xffffffffu;
+
+struct ProgCtl {
+    uint64_t full[kProgStages], empty[kProgStages];
+    uint64_t acc_full[2], acc_empty[2];
+    uint64_t tk_full[kProgTickets], tk_empty[kProgTickets];
+    uint32_t ticket[kProgTickets];
+    uint32_t stored[kProgTickets];            // epilogue warps that have stored their part of the tile
+    uint32_t tmem_base;
+    uint32_t abort;
+};
+static_assert(sizeof(ProgCtl) <= 1024, "control block");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void prog_decode(const ConvProgram& P, uint32_t item, int& l, int& b, int& tile) {
+    const int tpp = P.tiles_x * P.tiles_y;
+    const int per_layer = P.nbatch * tpp;
+    l = static_cast<int>(item / static_cast<uint32_t>(per_layer));
+    const int rem = static_cast<int>(item) - l * per_layer;
+    const int pair = rem / tpp;
+    tile = rem - pair * tpp;
+    b = P.b0 + pair;
+}
+
+// Waits for ticket slot n % kProgTickets and returns its ticket (kTicketEnd on time-out, which ends the role).
+__device__ __forceinline__ uint32_t prog_take_ticket(volatile ProgCtl* ctl, uint32_t n) {
+    const uint32_t slot = n % kProgTickets, par = (n / kProgTickets) & 1u;
+    if (!__all_sync(0xffffffffu, mbar_wait(const_cast<uint64_t*>(&ctl->tk_full[slot]), par))) {
+        ctl->abort = 50;
+        return kTicketEnd;
+    }
+    return ctl->ticket[slot];
+}
+__device__ __forceinline__ void prog_release_ticket(volatile ProgCtl* ctl, uint32_t n) {
+    __syncwarp();
+    if (elect_one()) mbar_arrive(const_cast<uint64_t*>(&ctl->tk_empty[n % kProgTickets]));
+}
+
+__global__ void __launch_bounds__(kProgThreads, 1)
+conv_prog_kernel(const __grid_constant__ ConvProgram P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    volatile ProgCtl* ctl = reinterpret_cast<volatile ProgCtl*>(smem + kProgCtlOff);
+    uint64_t* full = const_cast<uint64_t*>(ctl->full);
+    uint64_t* empty = const_cast<uint64_t*>(ctl->empty);
+    uint64_t* acc_full = const_cast<uint64_t*>(ctl->acc_full);
+    uint64_t* acc_empty = const_cast<uint64_t*>(ctl->acc_empty);
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kProgStages; ++s) {
+            mbar_init(&full[s], 2);              // A producer + B producer
+            mbar_init(&empty[s], 1);             // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);          // tcgen05.commit
+            mbar_init(&acc_empty[i], 8);         // one arrive per epilogue warp
+        }
+        for (int i = 0; i < kProgTickets; ++i) {
+            mbar_init(const_cast<uint64_t*>(&ctl->tk_full[i]), 1);      // scheduler
+            mbar_init(const_cast<uint64_t*>(&ctl->tk_empty[i]), 11);    // A, B, MMA + 8 epilogue warps
+            ctl->stored[i] = 0;
+        }
+        fence_mbar_init();
+        ctl->abort = 0;
+    }
+    if (threadIdx.x < 2 * P.n_layers) {
+        const ProgLayer& L = P.L[threadIdx.x >> 1];
+        tma_prefetch_desc((threadIdx.x & 1) ? &L.tmB : &L.tmA);
+    }
+    if (warp == 1) {
+        tmem_alloc(const_cast<uint32_t*>(&ctl->tmem_base), 512);     // two 256-column accumulators
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const uint32_t total = static_cast<uint32_t>(P.n_layers * P.nbatch * P.tiles_x * P.tiles_y);   // < 2^31 (host-checked)
+    const int tpp = P.tiles_x * P.tiles_y;
+
+    if (warp == 3) {
+        // ================= scheduler: ready queue in, tickets out, completions -> successor tiles ======================
+        const long set_elems = static_cast<long>(kMaxProgLayers) * P.max_batch * tpp;
+        int* arr_cur = P.arrivals + static_cast<long>(P.epoch & 1u) * set_elems;
+        {
+            int* arr_nxt = P.arrivals + static_cast<long>((P.epoch & 1u) ^ 1u) * set_elems;      // cleared for the next launch
+            for (long i = static_cast<long>(blockIdx.x) * 32 + lane; i < set_elems; i += static_cast<long>(gridDim.x) * 32) arr_nxt[i] = 0;
+        }
+        const unsigned long long tag = static_cast<unsigned long long>(P.epoch) << 32;
+        auto push = [&](uint32_t item) {
+            const unsigned long long slot = atomicAdd(P.tail, 1ull) - P.tail_base;
+            st_release_gpu_u64(P.queue + slot, tag | item);
+        };
+        const int per_layer = P.nbatch * tpp;
+        for (int l = 0; l < P.n_layers; ++l) {          // root layers: every tile is ready at launch
+            if (P.L[l].n_dep != 0) continue;
+            for (int r = static_cast<int>(blockIdx.x) * 32 + lane; r < per_layer; r += static_cast<int>(gridDim.x) * 32)
+                push(static_cast<uint32_t>(l * per_layer + r));
+        }
+        uint32_t n_issue = 0, n_done = 0, my_item = 0, idx = 0, spins = 0;
+        bool have_idx = false, end_posted = false;
+        for (;;) {
+            bool progress = false;
+            // ---- completed tiles of this CTA, in ticket order: count in at every successor tile, push those that become ready
+            while (n_done < n_issue) {
+                const uint32_t slot = n_done % kProgTickets;
+                uint32_t st;
+                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];"
+                             : "=r"(st) : "r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[slot]))) : "memory");
+                if (__shfl_sync(0xffffffffu, st, 0) != 8u) break;
+                const uint32_t item = __shfl_sync(0xffffffffu, my_item, static_cast<int>(slot));
+                int l, b, tile;
+                prog_decode(P, item, l, b, tile);
+                const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+                const ProgLayer& L = P.L[l];
+                if (lane < 18) {
+                    const int sl = lane < 9 ? L.succ0 : L.succ1;
+                    const int j = lane < 9 ? lane : lane - 9;
+                    const int nty = ty + j / 3 - 1, ntx = tx + j % 3 - 1;
+                    if (sl >= 0 && nty >= 0 && nty < P.tiles_y && ntx >= 0 && ntx < P.tiles_x) {
+                        const int nn = (1 + (ntx > 0) + (ntx < P.tiles_x - 1)) * (1 + (nty > 0) + (nty < P.tiles_y - 1));
+                        const int nt = nty * P.tiles_x + ntx;
+                        const int old = atom_add_acq_rel_gpu(arr_cur + (static_cast<long>(sl * P.max_batch + b) * tpp + nt), 1);
+                        if (old + 1 == P.L[sl].n_dep * nn) push(static_cast<uint32_t>((sl * P.nbatch + (b - P.b0)) * tpp + nt));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ctl->stored[slot] = 0;
+                ++n_done;
+                progress = true;
+            }
+            if (end_posted) {
+                if (n_done == n_issue) break;
+            } else if (n_issue - n_done < static_cast<uint32_t>(kProgTickets)) {
+                const uint32_t slot = n_issue % kProgTickets;
+                uint32_t room = 0;
+                if (lane == 0) room = mbar_try_wait(const_cast<uint64_t*>(&ctl->tk_empty[slot]), ((n_issue / kProgTickets) & 1u) ^ 1u) ? 1u : 0u;
+                if (__shfl_sync(0xffffffffu, room, 0) != 0u) {
+                    if (!have_idx) {
+                        if (lane == 0) {
+                            const unsigned long long d = atomicAdd(P.head, 1ull) - P.head_base;
+                            idx = d < total ? static_cast<uint32_t>(d) : kTicketEnd;
+                        }
+                        idx = __shfl_sync(0xffffffffu, idx, 0);
+                        have_idx = true;
+                        progress = true;
+                    }
+                    if (idx == kTicketEnd || ctl->abort != 0) {
+                        if (lane == 0) {
+                            ctl->ticket[slot] = kTicketEnd;
+                            mbar_arrive(const_cast<uint64_t*>(&ctl->tk_full[slot]));
+                        }
+                        end_posted = true;
+                        progress = true;
+                    } else {
+                        unsigned long long entry = 0;
+                        if (lane == 0) entry = ld_acquire_gpu_u64(P.queue + idx);
+                        entry = __shfl_sync(0xffffffffu, entry, 0);
+                        if ((entry >> 32) == P.epoch) {
+                            const uint32_t item = static_cast<uint32_t>(entry);
+                            fence_proxy_async_all();
+                            if (lane == static_cast<int>(slot)) my_item = item;
+                            if (lane == 0) {
+                                ctl->ticket[slot] = item;
+                                mbar_arrive(const_cast<uint64_t*>(&ctl->tk_full[slot]));   // release: ticket + everything acquired above
+                            }
+                            ++n_issue;
+                            have_idx = false;
+                            progress = true;
+                        }
+                    }
+                }
+            }
+            if (progress) {
+                spins = 0;
+            } else {
+                if (++spins > (1u << 21)) {
+                    ctl->abort = 70;
+                    if (spins > (1u << 21) + 64u) break;
+                }
+                __nanosleep(20);
+            }
+        }
+    } else if (warp == 0) {
+        // ================= A-operand producer ==========================================================================
+        uint32_t it_glob = 0;                    // stage counter over the whole launch: slot = it % 4, parity = (it / 4) & 1
+        for (uint32_t n = 0;; ++n) {
+            const uint32_t item = prog_take_ticket(ctl, n);
+            if (item == kTicketEnd) break;
+            int l, b, tile;
+            prog_decode(P, item, l, b, tile);
+            const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+            const ProgLayer& L = P.L[l];
+            const ConvGeom& g = L.g;
+            fence_proxy_async_all();
+            const int x0 = g.stride * tx * g.tile_w, y0 = g.stride * ty * g.tile_h;
+            const int rx = g.kw / 2, ry = g.kh / 2;
+            const int T = g.ntaps * g.kchunks;
+            int kc = 0, kx = 0, ky = 0;
+            bool ok = true;
+            for (int it = 0; it < T; ++it, ++it_glob) {
+                const uint32_t s = it_glob % kProgStages;
+                if (!__all_sync(0xffffffffu, mbar_wait(&empty[s], ((it_glob / kProgStages) & 1u) ^ 1u))) { ok = false; break; }
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[s], kTileM * 128);
+                    tma_load_4d(smem + s * kProgSlotBytes, &L.tmA, &full[s], kc * kChunkK, x0 + kx - rx, y0 + ky - ry, b);
+                }
+                __syncwarp();
+                if (++kc == g.kchunks) {
+                    kc = 0;
+                    if (++kx == g.kw) { kx = 0; ++ky; }
+                }
+            }
+            if (!ok) { ctl->abort = 1; break; }
+            prog_release_ticket(ctl, n);
+        }
+    } else if (warp == 2) {
+        // ================= B-operand producer ==========================================================================
+        uint32_t it_glob = 0;
+        for (uint32_t n = 0;; ++n) {
+            const uint32_t item = prog_take_ticket(ctl, n);
+            if (item == kTicketEnd) break;
+            int l, b, tile;
+            prog_decode(P, item, l, b, tile);
+            const ProgLayer& L = P.L[l];
+            const ConvGeom& g = L.g;
+            const int T = g.ntaps * g.kchunks;
+            const int brow = b * g.b_rows_per_batch;
+            const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
+            bool ok = true;
+            for (int it = 0; it < T; ++it, ++it_glob) {
+                const uint32_t s = it_glob % kProgStages;
+                if (!__all_sync(0xffffffffu, mbar_wait(&empty[s], ((it_glob / kProgStages) & 1u) ^ 1u))) { ok = false; break; }
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[s], b_bytes);
+                    tma_load_2d(smem + s * kProgSlotBytes + kTileM * 128, &L.tmB, &full[s], it * kChunkK, brow);
+                }
+                __syncwarp();
+            }
+            if (!ok) { ctl->abort = 3; break; }
+            prog_release_ticket(ctl, n);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer ==================================================================================
+        const uint32_t tmem_base = ctl->tmem_base;
+        const uint64_t d0 = umma_desc_k128(smem_u32(smem));
+        const uint32_t dhi = static_cast<uint32_t>(d0 >> 32), alo0 = static_cast<uint32_t>(d0);
+        uint32_t it_glob = 0;
+        long long t_ticket = 0, t_acc = 0, t_full = 0, t_all = clock64(), n_tiles = 0, n_stages = 0;
+        for (uint32_t n = 0;; ++n) {
+            long long t0 = clock64();
+            const uint32_t item = prog_take_ticket(ctl, n);
+            t_ticket += clock64() - t0;
+            if (item == kTicketEnd) break;
+            int l, b, tile;
+            prog_decode(P, item, l, b, tile);
+            const ConvGeom& g = P.L[l].g;
+            const int T = g.ntaps * g.kchunks;
+            const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
+            const uint32_t buf = n & 1u;
+            t0 = clock64();
+            bool ok = __all_sync(0xffffffffu, mbar_wait(&acc_empty[buf], ((n >> 1) & 1u) ^ 1u));     // accumulator drained
+            t_acc += clock64() - t0;
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * 256;
+            ++n_tiles;
+            n_stages += T;
+            for (int it = 0; ok && it < T; ++it, ++it_glob) {
+                const uint32_t s = it_glob % kProgStages;
+                t0 = clock64();
+                if (!__all_sync(0xffffffffu, mbar_wait(&full[s], (it_glob / kProgStages) & 1u))) { ok = false; break; }
+                t_full += clock64() - t0;
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t alo = alo0 + s * (kProgSlotBytes >> 4), blo = alo + ((kTileM * 128) >> 4);
+                    umma_f16_lohi(acc, alo, dhi, blo, dhi, idesc, it != 0 ? 1u : 0u);
+                    umma_f16_lohi(acc, alo + 2, dhi, blo + 2, dhi, idesc, 1u);
+                    umma_f16_lohi(acc, alo + 4, dhi, blo + 4, dhi, idesc, 1u);
+                    umma_f16_lohi(acc, alo + 6, dhi, blo + 6, dhi, idesc, 1u);
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+            }
+            if (!ok) { ctl->abort = 2; break; }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            prog_release_ticket(ctl, n);
+        }
+        if (lane == 0 && P.timing != nullptr) {
+            long long* o = P.timing + blockIdx.x * 16;
+            o[0] = clock64() - t_all; o[1] = t_ticket; o[2] = t_acc; o[3] = t_full; o[4] = n_tiles; o[5] = n_stages;
+        }
+    } else {
+        // ================= epilogue warps 4..11 ========================================================================
+        const int ew = warp - 4;
+        const uint32_t tmem_base = ctl->tmem_base;
+        long long e_ticket = 0, e_acc = 0, e_epi = 0, e_pub = 0;
+        for (uint32_t n = 0;; ++n) {
+            long long t0 = clock64();
+            const uint32_t item = prog_take_ticket(ctl, n);
+            e_ticket += clock64() - t0;
+            if (item == kTicketEnd) break;
+            int l, b, tile;
+            prog_decode(P, item, l, b, tile);
+            const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+            const ProgLayer& L = P.L[l];
+            const ConvGeom& g = L.g;
+            const ConvEpi& e = L.e;
+            const uint32_t buf = n & 1u;
+            t0 = clock64();
+            const bool ok_acc = __all_sync(0xffffffffu, mbar_wait(&acc_full[buf], (n >> 1) & 1u));
+            if (!ok_acc) ctl->abort = 4 + ew;      // keep going: the scheduler ends the launch
+            tc_fence_after();
+            e_acc += clock64() - t0;
+            t0 = clock64();
+            const uint32_t acc = tmem_base + buf * 256;
+            uint8_t* stg = smem + kProgStagingOff;
+            if (ok_acc) {
+                switch (L.mode) {
+                    case EPI_F16: tile_epilogue<EPI_F16, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    case EPI_F32: tile_epilogue<EPI_F32, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    case EPI_GRU_ZR: tile_epilogue<EPI_GRU_ZR, 1024, 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    case EPI_GRU_Q: tile_epilogue<EPI_GRU_Q, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    case EPI_FLOW: tile_epilogue<EPI_FLOW, 1024, 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    default: break;
+                }
+            }
+            e_epi += clock64() - t0;
+            t0 = clock64();
+            // accumulator free for tile n+2 as soon as this warp's TMEM loads are done (tcgen05.wait::ld inside)
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&acc_empty[buf]);
+            // every thread orders its generic-proxy stores before later async-proxy reads (TMA of a consumer tile), then the
+            // warp counts in (release); the scheduler acquires the count and announces the tile with gpu-scope acq_rel
+            // atomics, which are cumulative over everything the eight warps stored
+            fence_proxy_async_all();
+            __syncwarp();
+            if (elect_one())
+                asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;"
+                             ::"r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[n % kProgTickets]))) : "memory");
+            prog_release_ticket(ctl, n);
+            e_pub += clock64() - t0;
+        }
+        if (warp == 4 && lane == 0 && P.timing != nullptr) {
+            long long* o = P.timing + blockIdx.x * 16 + 8;
+            o[0] = e_ticket; o[1] = e_acc; o[2] = e_epi; o[3] = e_pub;
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && ctl->abort != 0 && P.err_flag != nullptr) atomicExch(P.err_flag, static_cast<int>(ctl->abort));
+    if (warp == 1) tmem_dealloc(ctl->tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -901,6 +1330,82 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
         cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, p.tmA, p.tmB, g, p.e);
         if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     }
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+// ------------------------------------------------------------------------------------------
+// layer programs (host side)
+// ------------------------------------------------------------------------------------------
+const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1) {
+    if (prog->n_layers >= kMaxProgLayers) return "conv_prog_add: too many layers";
+    const ConvGeom& g = p.g;
+    if (p.variant != 1 || g.cluster != 1 || g.n_tiles != 1) return "conv_prog_add: layer needs the plain 128-pixel kernel, one cout tile";
+    if (p.mode == EPI_CNET || p.e.stats != nullptr || p.e.res16 != nullptr) return "conv_prog_add: unsupported epilogue";
+    if (kTileM * 128 + g.n_tile * 128 > static_cast<int>(kProgSlotBytes)) return "conv_prog_add: stage does not fit a ring slot";
+    if (prog->n_layers == 0) {
+        prog->tiles_x = g.tiles_x;
+        prog->tiles_y = g.tiles_y;
+    } else if (prog->tiles_x != g.tiles_x || prog->tiles_y != g.tiles_y) {
+        return "conv_prog_add: layers of one program must share the tile grid";
+    }
+    if (dep0 >= prog->n_layers || dep1 >= prog->n_layers) return "conv_prog_add: dependency on a later layer";
+    const int self = prog->n_layers;
+    for (int d : {dep0, dep1}) {
+        if (d < 0) continue;
+        ProgLayer& D = prog->L[d];
+        if (D.succ0 < 0) D.succ0 = self;
+        else if (D.succ1 < 0) D.succ1 = self;
+        else return "conv_prog_add: a layer can feed at most two others";
+    }
+    ProgLayer& L = prog->L[prog->n_layers++];
+    L.tmA = p.tmA; L.tmB = p.tmB; L.g = p.g; L.e = p.e; L.mode = p.mode; L.dep0 = dep0; L.dep1 = dep1;
+    L.succ0 = L.succ1 = -1;
+    L.n_dep = (dep0 >= 0) + (dep1 >= 0);
+    L.g.b0 = 0;
+    return nullptr;
+}
+
+long conv_prog_items(const ConvProgram& prog, int nbatch) {
+    return static_cast<long>(prog.n_layers) * nbatch * prog.tiles_x * prog.tiles_y;
+}
+
+const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, cudaStream_t stream) {
+    static int n_sm = 0;
+    static bool attr_set = false;
+    const size_t smem = kProgSmemBytes + 1024;        // + alignment slack: 227 KiB in all, the per-CTA maximum
+    if (!attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t err = cudaFuncSetAttribute(conv_prog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err != cudaSuccess) return cudaGetErrorString(err);
+        attr_set = true;
+    }
+    if (nbatch < 1 || b0 < 0 || b0 + nbatch > prog->max_batch) return "conv_prog_launch: bad batch range";
+
+    const long total = conv_prog_items(*prog, nbatch);
+    long grid = n_sm;
+    if (grid > total) grid = total;
+    if (total > prog->queue_cap) return "conv_prog_launch: ready queue too small";
+    prog->nbatch = nbatch;
+    prog->b0 = b0;
+    prog->epoch += 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kProgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv_prog_kernel, *prog);
+    // every CTA pops until it sees a ticket >= total: head advances by total + grid per launch, tail by total
+    prog->head_base += static_cast<unsigned long long>(total + grid);
+    prog->tail_base += static_cast<unsigned long long>(total);
+    if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }

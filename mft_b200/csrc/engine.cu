@@ -94,6 +94,11 @@ struct mftb200_ctx {
     // run the pair batch as two concurrent half-batches; measured slower at 512^2 (204 vs 225 frames/s: twice the launches,
     // each with its own prologue / epilogue tail), so off by default -- kept as a tuning option, results are bit-identical
     int split_pairs = 0;
+    // one persistent launch per GRU iteration (tile-level dataflow between its 11 convolutions) instead of 11 launches
+    int persist = 1;
+    ConvProgram prog;
+    bool prog_ok = false;
+    int lookup_step = -1;
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
@@ -343,15 +348,17 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     Act a_fh{c->fhbuf, 256, 256, h, w};
     // motion encoder (update.py:152-160)
     // the correlation branch (caller's stream) and the flow branch (side stream) are independent until `conv`
+    // plan indices of the iteration's convolutions in program order, with their predecessor layers (conv_prog_kernel)
+    int pi[11];
     S.push_back(sync_step(1));
-    S.push_back(B.step(B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
-    S.push_back(B.step(B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
+    S.push_back(B.step(pi[0] = B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
+    S.push_back(B.step(pi[1] = B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
     S.back().lane = 1;
-    S.push_back(B.step(B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
-    S.push_back(B.step(B.conv16(L_CONVF2, a_f1, mp, 1, t3, 64, 1, c->cf, 256, 192, 64), true));
+    S.push_back(B.step(pi[2] = B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
+    S.push_back(B.step(pi[3] = B.conv16(L_CONVF2, a_f1, mp, 1, t3, 64, 1, c->cf, 256, 192, 64), true));
     S.back().lane = 1;
     S.push_back(sync_step(2));
-    S.push_back(B.step(B.conv16(L_CONVM, a_cf, mp, 1, t3, 128, 1, c->X, 512, 256, 126), true));
+    S.push_back(B.step(pi[4] = B.conv16(L_CONVM, a_cf, mp, 1, t3, 128, 1, c->X, 512, 256, 126), true));
     // SepConvGRU (update.py:108-123): horizontal 1x5 then vertical 5x1
     for (int pass = 0; pass < 2; ++pass) {
         const TapList& tp = pass == 0 ? t15 : t51;
@@ -361,15 +368,17 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             e.n_valid = 256; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 384;
         }
         S.push_back(B.step(izr, true));
+        pi[5 + 2 * pass] = izr;
         const int iq = B.conv(pass == 0 ? L_GRU_Q1 : L_GRU_Q2, a_qx, mp, 1, tp, 128, EPI_GRU_Q);
         if (iq >= 0) {
             ConvEpi& e = B.epi(iq);
             e.n_valid = 128; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 0;
         }
         S.push_back(B.step(iq, true));
+        pi[6 + 2 * pass] = iq;
     }
     // flow head (update.py:6-14) ; coords1 += delta_flow (core/raft.py:184)
-    S.push_back(B.step(B.conv16(L_FH1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    S.push_back(B.step(pi[9] = B.conv16(L_FH1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
     {
         const int i = B.conv(L_FH2, a_fh, mp, 1, t3, 16, EPI_FLOW);
         if (i >= 0) {
@@ -377,6 +386,31 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             e.n_valid = 2; e.coords1 = c->coords1; e.delta32 = c->delta32;
         }
         S.push_back(B.step(i, true));
+        pi[10] = i;
+    }
+    // the same 11 convolutions as ONE persistent launch with tile-level dataflow (see conv_prog_kernel):
+    // convc1, convf1 | convc2 <- convc1 | convf2 <- convf1 | convm <- convc2, convf2 | zr1 <- convm | q1 <- zr1 |
+    // zr2 <- q1 | q2 <- zr2 | fh1 <- q2 | fh2 <- fh1   (3x3 tile neighbourhood of each predecessor)
+    c->prog_ok = false;
+    if (!B.err) {
+        static const int deps[11][2] = {{-1, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, 3}, {4, -1}, {5, -1}, {6, -1},
+                                        {7, -1}, {8, -1}, {9, -1}};
+        memset(&c->prog, 0, sizeof c->prog);
+        const char* pe = nullptr;
+        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], deps[k][0], deps[k][1]);
+        if (!pe) {
+            c->prog.max_batch = mp;
+            c->prog.err_flag = c->err_flag;
+            const size_t tiles = static_cast<size_t>(c->prog.tiles_x) * c->prog.tiles_y;
+            unsigned long long* hq = c->dalloc<unsigned long long>(64);
+            c->prog.head = hq;
+            c->prog.tail = hq ? hq + 16 : nullptr;
+            c->prog.queue_cap = static_cast<int>(kMaxProgLayers * mp * tiles);
+            c->prog.queue = c->dalloc<unsigned long long>(c->prog.queue_cap);
+            c->prog.arrivals = c->dalloc<int>(2 * static_cast<size_t>(kMaxProgLayers) * mp * tiles);
+            c->prog.timing = c->dalloc<long long>(8 * 1024);
+            c->prog_ok = hq != nullptr && c->prog.queue != nullptr && c->prog.arrivals != nullptr;
+        }
     }
 
     // ---- after the last iteration: mask head || OU head (independent until the upsampling), convex upsampling --------
@@ -706,7 +740,22 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
         cudaStreamWaitEvent(c->gs[1][0], c->ev_start, 0);
     }
     int r = run_steps_groups(c, c->pre_steps, groups, n_groups);
-    for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) r = run_steps_groups(c, c->iter_steps, groups, n_groups);
+    const bool persist = c->persist && c->prog_ok && n_groups == 1 && !c->conv_impl;
+    for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) {
+        if (!persist) {
+            r = run_steps_groups(c, c->iter_steps, groups, n_groups);
+            continue;
+        }
+        c->cur_group = 0; c->cur_b0 = 0; c->cur_pairs = n_pairs;
+        r = run_one(c, c->iter_steps[0]);                       // pyramid lookup
+        if (r != MFTB200_OK) break;
+        mftb200_ctx::Step prog_step([](mftb200_ctx* cc, cudaStream_t st) -> const char* {
+            cc->launches++;
+            return conv_prog_launch(&cc->prog, cc->cur_pairs, 0, st);
+        }, 0);
+        prog_step.tag = 200;                                     // the iteration program
+        r = run_one(c, prog_step);
+    }
     if (r == MFTB200_OK) r = run_steps_groups(c, c->final_steps, groups, n_groups);
     if (n_groups == 2) {
         cudaEventRecord(c->ev_done, c->gs[1][0]);
@@ -768,6 +817,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "persist") == 0) { c->persist = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
@@ -831,7 +881,7 @@ int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* b
         {"corr_l3", c->corr[3], c->corr_bytes[3]}, {"corr16", c->corr16, M * 328 * 2}, {"X", c->X, M * 512 * 2},
         {"h32", c->h32, M * 128 * 4}, {"coords1", c->coords1, M * 2 * 4}, {"delta32", c->delta32, M * 2 * 4},
         {"mask32", c->mask32, M * 576 * 4}, {"ou32", c->ou32, M * 4 * 4}, {"patches", c->patches, 0},
-        {"E0", c->E[0], 0}, {"E1", c->E[1], 0}, {"flowpatch", c->flowpatch, M * 104 * 2}, {"cf", c->cf, M * 256 * 2},
+        {"prog_timing", c->prog.timing, 8 * 1024 * 8}, {"E0", c->E[0], 0}, {"E1", c->E[1], 0}, {"flowpatch", c->flowpatch, M * 104 * 2}, {"cf", c->cf, M * 256 * 2},
     };
     for (const Ent& e : tab)
         if (strcmp(e.n, name) == 0) { *ptr = e.p; *bytes = e.b; return MFTB200_OK; }

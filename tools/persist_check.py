@@ -1,0 +1,55 @@
+"""Persistent layer-program kernel vs one launch per layer: bit-exact outputs + device time of one refinement."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from mft_b200 import engine as E  # noqa: E402
+from mft_b200.synth import synthetic_video  # noqa: E402
+
+size = int(os.environ.get('CHECK_SIZE', '512'))
+pairs = int(os.environ.get('CHECK_PAIRS', '7'))
+reps = int(os.environ.get('CHECK_REPS', '5'))
+weights, _ = bench.load_weights()
+eng = E.Engine(weights)
+eng.configure(size, size, max_pairs=pairs, n_slots=pairs + 2, iters=12)
+frames = list(synthetic_video(pairs + 1, size, size, seed=5))
+for i, f in enumerate(frames):
+    eng.encode_frame(f, i)
+lefts, rights = list(range(pairs)), [pairs] * pairs
+res = {}
+for mode in (0, 1, 0, 1):
+    eng.set_option('persist', mode)
+    out = eng.refine(lefts, rights)
+    eng.check_device()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = eng.refine(lefts, rights)
+    b.record()
+    torch.cuda.synchronize()
+    eng.check_device()
+    ms = a.elapsed_time(b) / reps
+    print(f'persist={mode}: {ms:.3f} ms per {pairs}-pair refinement, finite={bool(torch.isfinite(out).all())}', flush=True)
+    if mode in res:
+        print(f'   repeatable: {bool(torch.equal(res[mode], out))}')
+    res[mode] = out.clone()
+d = (res[0] - res[1]).abs()
+print(f'persist vs layered: bit-identical={bool(torch.equal(res[0], res[1]))} max|diff|={d.max().item():.3e} '
+      f'flow mean|diff|={d[:, :2].mean().item():.3e}')
+
+eng.set_option('persist', 1)
+out = eng.refine(lefts, rights)
+t = eng.debug_buffer('prog_timing', torch.int64, (512, 16)).cpu().numpy().astype(float)
+t = t[t[:, 4] > 0]
+us = lambda c: c / 1.965e3
+print(f'{len(t)} CTAs; MMA warp: {us(t[:, 0].mean()):.1f} us in the launch, {t[:, 4].mean():.1f} tiles, {t[:, 5].mean():.0f} stages per CTA')
+print(f'   MMA warp waits: ticket {us(t[:, 1].mean()):.1f} us, accumulator free {us(t[:, 2].mean()):.1f} us, '
+      f'operands {us(t[:, 3].mean()):.1f} us ({t[:, 3].sum() / t[:, 5].sum():.0f} cycles per stage); '
+      f'issue+rest {us((t[:, 0] - t[:, 1] - t[:, 2] - t[:, 3]).mean()):.1f} us')
+print(f'   epilogue warp 4: ticket {us(t[:, 8].mean()):.1f} us, accumulator ready {us(t[:, 9].mean()):.1f} us, '
+      f'epilogue {us(t[:, 10].mean()):.1f} us ({t[:, 10].sum() / t[:, 4].sum():.0f} cycles per tile), publish {us(t[:, 11].mean()):.1f} us')
