@@ -158,6 +158,32 @@ def test_split_half_batches_bit_identical(seeded_weights):
     assert torch.equal(ref, got)
 
 
+@pytest.mark.parametrize('geom', [(128, 160, 5), (136, 200, 2), (256, 256, 7), (512, 512, 7)])
+def test_persistent_program_bit_identical(geom, seeded_weights):
+    """The persistent layer-program kernel (one launch per GRU iteration, tile-level dataflow between the 11
+    convolutions, default) against one launch per layer: same arithmetic in the same order, so not a single bit may
+    differ -- a dependency or memory-ordering bug between tiles would show up here.  Repeated to catch races; the pair
+    count changes between calls (the ready queue and arrival counters carry state from launch to launch)."""
+    from mft_b200.synth import synthetic_video
+    H, Wd, pairs = geom
+    frames = list(synthetic_video(pairs + 1, H, Wd, seed=21))
+    eng = _engine(seeded_weights, H, Wd, pairs=pairs, slots=pairs + 1)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    lefts, rights = list(range(pairs)), [pairs] * pairs
+    eng.set_option('persist', 0)
+    ref = eng.refine(lefts, rights).clone()
+    ref1 = eng.refine(lefts[:1], rights[:1]).clone()
+    eng.set_option('persist', 1)
+    for rep in range(3):
+        got = eng.refine(lefts, rights).clone()
+        eng.check_device()
+        assert torch.equal(ref, got), (geom, rep, (ref - got).abs().max().item())
+        got1 = eng.refine(lefts[:1], rights[:1]).clone()
+        eng.check_device()
+        assert torch.equal(ref1, got1), (geom, rep)
+
+
 def test_tracker_vs_oracle_real_128(real_weights):
     """mft_b200.MFT.MFT against the oracle tracker and the reference tracker's golden results."""
     from mft_b200.config import Config
