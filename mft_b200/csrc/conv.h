@@ -12,6 +12,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include "kernels.h"
+
 namespace mftb {
 
 enum EpiMode : int {
@@ -116,7 +118,8 @@ struct ProgLayer {
     int dep0, dep1;               // program layers whose 3x3 tile neighbourhood (same batch entry) must be complete, -1 = none
     int succ0, succ1;             // layers that list this one as a dependency (filled by conv_prog_add), -1 = none
     int n_dep;                    // number of valid dependencies (0 = root layer: its tiles are ready at launch)
-    int pad_[2];
+    int kind;                     // 0 = convolution, 1 = correlation-pyramid lookup tile (no MMA; run by the epilogue warps)
+    int iter_shift;               // 1: the dependencies are the PREVIOUS iteration's tiles (iteration 0 is ready at launch)
 };
 
 // Work distribution is a dataflow ready queue in global memory: a tile is pushed when the last of its predecessor
@@ -125,6 +128,8 @@ struct ProgLayer {
 struct ConvProgram {
     ProgLayer L[kMaxProgLayers];
     int n_layers;
+    int iters;                    // the whole layer sequence is repeated `iters` times (iterations overlap tile by tile)
+    LookupArgs lk;                // operands of the lookup layer, if any
     int nbatch, b0;               // batch entries covered by this launch
     int max_batch;                // counter-array pitch
     int tiles_x, tiles_y;         // common to every layer
@@ -141,9 +146,14 @@ struct ConvProgram {
 
 // Appends plan `p` as the next layer of `prog` (checks the common geometry).  Returns nullptr or an error string.
 const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1);
-// One launch for the whole program; updates prog->epoch / counter_base for the next launch.
-const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, cudaStream_t stream);
-// Work items (= tile launches folded into the program) of a launch with `nbatch` batch entries.
+// Appends a lookup layer (tile geometry of `like`) that depends on layer `dep` of the PREVIOUS iteration (a later
+// layer of the sequence, wired up by conv_prog_finish).
+const char* conv_prog_add_lookup(ConvProgram* prog, const ConvPlan& like, const LookupArgs& lk, int dep_prev_iter);
+// Resolves the successor lists once all layers are added.
+const char* conv_prog_finish(ConvProgram* prog);
+// One launch for `iters` repetitions of the whole program; updates prog->epoch / bases for the next launch.
+const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, int iters, cudaStream_t stream);
+// Work items (= tile launches folded into the program) of one iteration with `nbatch` batch entries.
 long conv_prog_items(const ConvProgram& prog, int nbatch);
 
 // Launch on `stream`; nbatch <= batch given at init.  use_simt=1 runs the SIMT cross-check kernel.

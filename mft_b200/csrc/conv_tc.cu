@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "conv.h"
+#include "lookup.cuh"
 #include "ptx.cuh"
 
 namespace mftb {
@@ -492,14 +493,44 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ void prog_decode(const ConvProgram& P, uint32_t item, int& l, int& b, int& tile) {
+// Correlation-pyramid lookup of one tile's 128 pixels by the 8 epilogue warps: 16 pixels per warp, two in flight (2 x 1664 B
+// of the warp's staging area hold their windows).  Out of line: its registers are then allocated apart from the
+// convolution epilogues' (a spill costs an L2 round trip here -- the L1 is carved out for shared memory).
+__device__ __noinline__ void prog_lookup_tile(const LookupArgs& lk, const ConvGeom& g, float* win, int ew, int lane, int tx,
+                                              int ty, int b) {
+    for (int r = 0; r < 16; r += 2) {
+        long pp[2];
+        LookupPixel px[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int row = ew * 16 + r + u;
+            const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & (g.tile_w - 1));
+            pp[u] = (y < g.H && x < g.W) ? (static_cast<long>(b) * g.H + y) * g.W + x : -1;
+            if (pp[u] >= 0) lookup_gather(lk, pp[u], lane, win + u * kLkWinFloats, px[u]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (pp[u] >= 0) lookup_emit(lk, pp[u], lane, win + u * kLkWinFloats, px[u]);
+        __syncwarp();
+    }
+}
+
+// item = ((iteration * n_layers + layer) * nbatch + batch) * tiles + tile
+__device__ __forceinline__ void prog_decode(const ConvProgram& P, uint32_t item, int& it, int& l, int& b, int& tile) {
     const int tpp = P.tiles_x * P.tiles_y;
     const int per_layer = P.nbatch * tpp;
-    l = static_cast<int>(item / static_cast<uint32_t>(per_layer));
-    const int rem = static_cast<int>(item) - l * per_layer;
+    const int il = static_cast<int>(item / static_cast<uint32_t>(per_layer));
+    const int rem = static_cast<int>(item) - il * per_layer;
+    it = il / P.n_layers;
+    l = il - it * P.n_layers;
     const int pair = rem / tpp;
     tile = rem - pair * tpp;
     b = P.b0 + pair;
+}
+__device__ __forceinline__ void prog_decode(const ConvProgram& P, uint32_t item, int& l, int& b, int& tile) {
+    int it;
+    prog_decode(P, item, it, l, b, tile);
 }
 
 // Waits for ticket slot n % kProgTickets and returns its ticket (kTicketEnd on time-out, which ends the role).
@@ -516,6 +547,8 @@ __device__ __forceinline__ void prog_release_ticket(volatile ProgCtl* ctl, uint3
     if (elect_one()) mbar_arrive(const_cast<uint64_t*>(&ctl->tk_empty[n % kProgTickets]));
 }
 
+// LOOKUP: the program may contain a lookup layer (compiled apart: its code would only cost the plain program registers)
+template <bool LOOKUP>
 __global__ void __launch_bounds__(kProgThreads, 1)
 conv_prog_kernel(const __grid_constant__ ConvProgram P) {
     extern __shared__ uint8_t smem_raw[];
@@ -559,7 +592,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
     pdl_launch_dependents();
     pdl_wait();
 
-    const uint32_t total = static_cast<uint32_t>(P.n_layers * P.nbatch * P.tiles_x * P.tiles_y);   // < 2^31 (host-checked)
+    const uint32_t total = static_cast<uint32_t>(P.iters * P.n_layers * P.nbatch * P.tiles_x * P.tiles_y);   // < 2^31 (host-checked)
     const int tpp = P.tiles_x * P.tiles_y;
 
     if (warp == 3) {
@@ -576,8 +609,8 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             st_release_gpu_u64(P.queue + slot, tag | item);
         };
         const int per_layer = P.nbatch * tpp;
-        for (int l = 0; l < P.n_layers; ++l) {          // root layers: every tile is ready at launch
-            if (P.L[l].n_dep != 0) continue;
+        for (int l = 0; l < P.n_layers; ++l) {          // roots: iteration 0 of the layers without same-iteration predecessors
+            if (P.L[l].n_dep != 0 && P.L[l].iter_shift == 0) continue;
             for (int r = static_cast<int>(blockIdx.x) * 32 + lane; r < per_layer; r += static_cast<int>(gridDim.x) * 32)
                 push(static_cast<uint32_t>(l * per_layer + r));
         }
@@ -593,8 +626,8 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                              : "=r"(st) : "r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[slot]))) : "memory");
                 if (__shfl_sync(0xffffffffu, st, 0) != 8u) break;
                 const uint32_t item = __shfl_sync(0xffffffffu, my_item, static_cast<int>(slot));
-                int l, b, tile;
-                prog_decode(P, item, l, b, tile);
+                int it, l, b, tile;
+                prog_decode(P, item, it, l, b, tile);
                 const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
                 const ProgLayer& L = P.L[l];
                 if (lane < 18) {
@@ -602,10 +635,18 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                     const int j = lane < 9 ? lane : lane - 9;
                     const int nty = ty + j / 3 - 1, ntx = tx + j % 3 - 1;
                     if (sl >= 0 && nty >= 0 && nty < P.tiles_y && ntx >= 0 && ntx < P.tiles_x) {
-                        const int nn = (1 + (ntx > 0) + (ntx < P.tiles_x - 1)) * (1 + (nty > 0) + (nty < P.tiles_y - 1));
-                        const int nt = nty * P.tiles_x + ntx;
-                        const int old = atom_add_acq_rel_gpu(arr_cur + (static_cast<long>(sl * P.max_batch + b) * tpp + nt), 1);
-                        if (old + 1 == P.L[sl].n_dep * nn) push(static_cast<uint32_t>((sl * P.nbatch + (b - P.b0)) * tpp + nt));
+                        // the successor tile of iteration `its` is ready when all (its - shift + 1) rounds of arrivals are in
+                        // (a round = every predecessor layer x every tile of the 3x3 neighbourhood); rounds cannot mix because
+                        // round r+1 only starts arriving after the tile itself has run in round r (it is their ancestor)
+                        const ProgLayer& S = P.L[sl];
+                        const int its = it + S.iter_shift;
+                        if (its < P.iters) {
+                            const int nn = (1 + (ntx > 0) + (ntx < P.tiles_x - 1)) * (1 + (nty > 0) + (nty < P.tiles_y - 1));
+                            const int nt = nty * P.tiles_x + ntx;
+                            const int old = atom_add_acq_rel_gpu(arr_cur + (static_cast<long>(sl * P.max_batch + b) * tpp + nt), 1);
+                            if (old + 1 == (it + 1) * S.n_dep * nn)
+                                push(static_cast<uint32_t>(((its * P.n_layers + sl) * P.nbatch + (b - P.b0)) * tpp + nt));
+                        }
                     }
                 }
                 __syncwarp();
@@ -679,7 +720,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             fence_proxy_async_all();
             const int x0 = g.stride * tx * g.tile_w, y0 = g.stride * ty * g.tile_h;
             const int rx = g.kw / 2, ry = g.kh / 2;
-            const int T = g.ntaps * g.kchunks;
+            const int T = L.kind == 0 ? g.ntaps * g.kchunks : 0;        // lookup tiles have no operands
             int kc = 0, kx = 0, ky = 0;
             bool ok = true;
             for (int it = 0; it < T; ++it, ++it_glob) {
@@ -708,7 +749,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             prog_decode(P, item, l, b, tile);
             const ProgLayer& L = P.L[l];
             const ConvGeom& g = L.g;
-            const int T = g.ntaps * g.kchunks;
+            const int T = L.kind == 0 ? g.ntaps * g.kchunks : 0;
             const int brow = b * g.b_rows_per_batch;
             const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
             bool ok = true;
@@ -739,7 +780,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             int l, b, tile;
             prog_decode(P, item, l, b, tile);
             const ConvGeom& g = P.L[l].g;
-            const int T = g.ntaps * g.kchunks;
+            const int T = P.L[l].kind == 0 ? g.ntaps * g.kchunks : 0;   // lookup tile: just hand the (unused) accumulator over
             const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
             const uint32_t buf = n & 1u;
             t0 = clock64();
@@ -776,12 +817,8 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
     } else {
         // ================= epilogue warps 4..11 ========================================================================
         const int ew = warp - 4;
-        const uint32_t tmem_base = ctl->tmem_base;
-        long long e_ticket = 0, e_acc = 0, e_epi = 0, e_pub = 0;
         for (uint32_t n = 0;; ++n) {
-            long long t0 = clock64();
             const uint32_t item = prog_take_ticket(ctl, n);
-            e_ticket += clock64() - t0;
             if (item == kTicketEnd) break;
             int l, b, tile;
             prog_decode(P, item, l, b, tile);
@@ -790,26 +827,28 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             const ConvGeom& g = L.g;
             const ConvEpi& e = L.e;
             const uint32_t buf = n & 1u;
-            t0 = clock64();
             const bool ok_acc = __all_sync(0xffffffffu, mbar_wait(&acc_full[buf], (n >> 1) & 1u));
             if (!ok_acc) ctl->abort = 4 + ew;      // keep going: the scheduler ends the launch
             tc_fence_after();
-            e_acc += clock64() - t0;
-            t0 = clock64();
-            const uint32_t acc = tmem_base + buf * 256;
+            const uint32_t acc = ctl->tmem_base + buf * 256;
             uint8_t* stg = smem + kProgStagingOff;
-            if (ok_acc) {
+            if (LOOKUP && ok_acc && L.kind == 1) {
+                const long long t0 = clock64();
+                prog_lookup_tile(P.lk, g, reinterpret_cast<float*>(stg) + ew * 1024, ew, lane, tx, ty, b);
+                if (warp == 4 && lane == 0 && P.timing != nullptr) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(P.timing + blockIdx.x * 16 + 8), static_cast<unsigned long long>(clock64() - t0));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(P.timing + blockIdx.x * 16 + 9), 1ull);
+                }
+            } else if (ok_acc) {
                 switch (L.mode) {
                     case EPI_F16: tile_epilogue<EPI_F16, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
                     case EPI_F32: tile_epilogue<EPI_F32, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
-                    case EPI_GRU_ZR: tile_epilogue<EPI_GRU_ZR, 1024, 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    case EPI_GRU_ZR: tile_epilogue<EPI_GRU_ZR, 1024, LOOKUP ? 1 : 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
                     case EPI_GRU_Q: tile_epilogue<EPI_GRU_Q, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
                     case EPI_FLOW: tile_epilogue<EPI_FLOW, 1024, 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
                     default: break;
                 }
             }
-            e_epi += clock64() - t0;
-            t0 = clock64();
             // accumulator free for tile n+2 as soon as this warp's TMEM loads are done (tcgen05.wait::ld inside)
             tc_fence_before();
             __syncwarp();
@@ -823,11 +862,6 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                 asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;"
                              ::"r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[n % kProgTickets]))) : "memory");
             prog_release_ticket(ctl, n);
-            e_pub += clock64() - t0;
-        }
-        if (warp == 4 && lane == 0 && P.timing != nullptr) {
-            long long* o = P.timing + blockIdx.x * 16 + 8;
-            o[0] = e_ticket; o[1] = e_acc; o[2] = e_epi; o[3] = e_pub;
         }
     }
     __syncwarp();
@@ -1350,19 +1384,53 @@ const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int de
         return "conv_prog_add: layers of one program must share the tile grid";
     }
     if (dep0 >= prog->n_layers || dep1 >= prog->n_layers) return "conv_prog_add: dependency on a later layer";
-    const int self = prog->n_layers;
-    for (int d : {dep0, dep1}) {
-        if (d < 0) continue;
-        ProgLayer& D = prog->L[d];
-        if (D.succ0 < 0) D.succ0 = self;
-        else if (D.succ1 < 0) D.succ1 = self;
-        else return "conv_prog_add: a layer can feed at most two others";
-    }
     ProgLayer& L = prog->L[prog->n_layers++];
     L.tmA = p.tmA; L.tmB = p.tmB; L.g = p.g; L.e = p.e; L.mode = p.mode; L.dep0 = dep0; L.dep1 = dep1;
     L.succ0 = L.succ1 = -1;
     L.n_dep = (dep0 >= 0) + (dep1 >= 0);
+    L.kind = 0;
+    L.iter_shift = 0;
     L.g.b0 = 0;
+    return nullptr;
+}
+
+const char* conv_prog_add_lookup(ConvProgram* prog, const ConvPlan& like, const LookupArgs& lk, int dep_prev_iter) {
+    if (prog->n_layers >= kMaxProgLayers) return "conv_prog_add_lookup: too many layers";
+    const ConvGeom& g = like.g;
+    if (prog->n_layers == 0) {
+        prog->tiles_x = g.tiles_x;
+        prog->tiles_y = g.tiles_y;
+    } else if (prog->tiles_x != g.tiles_x || prog->tiles_y != g.tiles_y) {
+        return "conv_prog_add_lookup: layers of one program must share the tile grid";
+    }
+    ProgLayer& L = prog->L[prog->n_layers++];
+    memset(&L, 0, sizeof L);
+    L.g = like.g;
+    L.g.b0 = 0;
+    L.mode = EPI_F16;
+    L.dep0 = dep_prev_iter; L.dep1 = -1;
+    L.succ0 = L.succ1 = -1;
+    L.n_dep = 1;
+    L.kind = 1;
+    L.iter_shift = 1;
+    prog->lk = lk;
+    return nullptr;
+}
+
+const char* conv_prog_finish(ConvProgram* prog) {
+    for (int i = 0; i < prog->n_layers; ++i) prog->L[i].succ0 = prog->L[i].succ1 = -1;
+    for (int i = 0; i < prog->n_layers; ++i) {
+        const ProgLayer& L = prog->L[i];
+        for (int d : {L.dep0, L.dep1}) {
+            if (d < 0) continue;
+            if (d >= prog->n_layers) return "conv_prog_finish: dependency on a missing layer";
+            if (L.iter_shift == 0 && d >= i) return "conv_prog_finish: same-iteration dependency on a later layer";
+            ProgLayer& D = prog->L[d];
+            if (D.succ0 < 0) D.succ0 = i;
+            else if (D.succ1 < 0) D.succ1 = i;
+            else return "conv_prog_finish: a layer can feed at most two others";
+        }
+    }
     return nullptr;
 }
 
@@ -1370,7 +1438,7 @@ long conv_prog_items(const ConvProgram& prog, int nbatch) {
     return static_cast<long>(prog.n_layers) * nbatch * prog.tiles_x * prog.tiles_y;
 }
 
-const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, cudaStream_t stream) {
+const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, int iters, cudaStream_t stream) {
     static int n_sm = 0;
     static bool attr_set = false;
     const size_t smem = kProgSmemBytes + 1024;        // + alignment slack: 227 KiB in all, the per-CTA maximum
@@ -1378,18 +1446,23 @@ const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, cudaStream_t
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t err = cudaFuncSetAttribute(conv_prog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t err = cudaFuncSetAttribute(conv_prog_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_prog_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (err != cudaSuccess) return cudaGetErrorString(err);
         attr_set = true;
     }
     if (nbatch < 1 || b0 < 0 || b0 + nbatch > prog->max_batch) return "conv_prog_launch: bad batch range";
 
-    const long total = conv_prog_items(*prog, nbatch);
+    if (iters < 1) return "conv_prog_launch: bad iteration count";
+    for (int i = 0; i < prog->n_layers; ++i)
+        if (iters > 1 && prog->L[i].n_dep == 0) return "conv_prog_launch: a root layer cannot be iterated";
+    const long total = conv_prog_items(*prog, nbatch) * iters;
     long grid = n_sm;
     if (grid > total) grid = total;
     if (total > prog->queue_cap) return "conv_prog_launch: ready queue too small";
     prog->nbatch = nbatch;
     prog->b0 = b0;
+    prog->iters = iters;
     prog->epoch += 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -1401,7 +1474,10 @@ const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, cudaStream_t
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv_prog_kernel, *prog);
+    bool has_lookup = false;
+    for (int i = 0; i < prog->n_layers; ++i) has_lookup = has_lookup || prog->L[i].kind == 1;
+    cudaError_t lerr = has_lookup ? cudaLaunchKernelEx(&cfg, conv_prog_kernel<true>, *prog)
+                                  : cudaLaunchKernelEx(&cfg, conv_prog_kernel<false>, *prog);
     // every CTA pops until it sees a ticket >= total: head advances by total + grid per launch, tail by total
     prog->head_base += static_cast<unsigned long long>(total + grid);
     prog->tail_base += static_cast<unsigned long long>(total);

@@ -95,9 +95,11 @@ struct mftb200_ctx {
     // each with its own prologue / epilogue tail), so off by default -- kept as a tuning option, results are bit-identical
     int split_pairs = 0;
     // one persistent launch per GRU iteration (tile-level dataflow between its 11 convolutions) instead of 11 launches
+    // 1 = one launch per iteration (default), 2 = ONE launch for all iterations with the pyramid lookup as tiles of the
+    // program (correct, but the lookup is latency-bound on 8 warps per SM: slower, kept as an option under test)
     int persist = 1;
-    ConvProgram prog;
-    bool prog_ok = false;
+    ConvProgram prog, prog_full;
+    bool prog_ok = false, prog_full_ok = false;
     int lookup_step = -1;
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
@@ -391,26 +393,37 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     // the same 11 convolutions as ONE persistent launch with tile-level dataflow (see conv_prog_kernel):
     // convc1, convf1 | convc2 <- convc1 | convf2 <- convf1 | convm <- convc2, convf2 | zr1 <- convm | q1 <- zr1 |
     // zr2 <- q1 | q2 <- zr2 | fh1 <- q2 | fh2 <- fh1   (3x3 tile neighbourhood of each predecessor)
-    c->prog_ok = false;
+    c->prog_ok = c->prog_full_ok = false;
     if (!B.err) {
-        static const int deps[11][2] = {{-1, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, 3}, {4, -1}, {5, -1}, {6, -1},
-                                        {7, -1}, {8, -1}, {9, -1}};
+        // program A: the 11 convolutions of one iteration (roots convc1, convf1; the lookup runs as its own kernel before)
+        // program B: lookup (fed by the previous iteration's flow head) + the 11 convolutions, iterated inside ONE launch
+        static const int depsA[11][2] = {{-1, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, 3}, {4, -1}, {5, -1}, {6, -1},
+                                         {7, -1}, {8, -1}, {9, -1}};
+        static const int depsB[11][2] = {{0, -1}, {0, -1}, {1, -1}, {2, -1}, {3, 4}, {5, -1}, {6, -1}, {7, -1},
+                                         {8, -1}, {9, -1}, {10, -1}};
+        auto finish = [&](ConvProgram& P, int iters_cap) -> bool {
+            if (conv_prog_finish(&P)) return false;
+            P.max_batch = mp;
+            P.err_flag = c->err_flag;
+            const size_t tiles = static_cast<size_t>(P.tiles_x) * P.tiles_y;
+            unsigned long long* hq = c->dalloc<unsigned long long>(64);
+            P.head = hq;
+            P.tail = hq ? hq + 16 : nullptr;
+            P.queue_cap = static_cast<int>(iters_cap * kMaxProgLayers * mp * tiles);
+            P.queue = c->dalloc<unsigned long long>(P.queue_cap);
+            P.arrivals = c->dalloc<int>(2 * static_cast<size_t>(kMaxProgLayers) * mp * tiles);
+            P.timing = c->dalloc<long long>(8 * 1024);
+            return hq != nullptr && P.queue != nullptr && P.arrivals != nullptr && P.timing != nullptr;
+        };
         memset(&c->prog, 0, sizeof c->prog);
         const char* pe = nullptr;
-        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], deps[k][0], deps[k][1]);
-        if (!pe) {
-            c->prog.max_batch = mp;
-            c->prog.err_flag = c->err_flag;
-            const size_t tiles = static_cast<size_t>(c->prog.tiles_x) * c->prog.tiles_y;
-            unsigned long long* hq = c->dalloc<unsigned long long>(64);
-            c->prog.head = hq;
-            c->prog.tail = hq ? hq + 16 : nullptr;
-            c->prog.queue_cap = static_cast<int>(kMaxProgLayers * mp * tiles);
-            c->prog.queue = c->dalloc<unsigned long long>(c->prog.queue_cap);
-            c->prog.arrivals = c->dalloc<int>(2 * static_cast<size_t>(kMaxProgLayers) * mp * tiles);
-            c->prog.timing = c->dalloc<long long>(8 * 1024);
-            c->prog_ok = hq != nullptr && c->prog.queue != nullptr && c->prog.arrivals != nullptr;
-        }
+        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], depsA[k][0], depsA[k][1]);
+        if (!pe) c->prog_ok = finish(c->prog, 1);
+        memset(&c->prog_full, 0, sizeof c->prog_full);
+        LookupArgs lk{{c->corr[0], c->corr[1], c->corr[2], c->corr[3]}, c->coords1, c->corr16, c->flowpatch, c->X, mp, h, w};
+        pe = conv_prog_add_lookup(&c->prog_full, c->plans[pi[0]], lk, 11);
+        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog_full, c->plans[pi[k]], depsB[k][0], depsB[k][1]);
+        if (!pe) c->prog_full_ok = finish(c->prog_full, 64);
     }
 
     // ---- after the last iteration: mask head || OU head (independent until the upsampling), convex upsampling --------
@@ -740,21 +753,32 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
         cudaStreamWaitEvent(c->gs[1][0], c->ev_start, 0);
     }
     int r = run_steps_groups(c, c->pre_steps, groups, n_groups);
-    const bool persist = c->persist && c->prog_ok && n_groups == 1 && !c->conv_impl;
-    for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) {
-        if (!persist) {
-            r = run_steps_groups(c, c->iter_steps, groups, n_groups);
-            continue;
-        }
+    const bool layered = n_groups != 1 || c->conv_impl || c->persist == 0;
+    if (!layered && c->persist == 2 && c->prog_full_ok && c->iters <= 64 && r == MFTB200_OK) {
+        // all iterations in ONE launch: lookup + 11 convolutions per iteration as tiles of one dataflow program
         c->cur_group = 0; c->cur_b0 = 0; c->cur_pairs = n_pairs;
-        r = run_one(c, c->iter_steps[0]);                       // pyramid lookup
-        if (r != MFTB200_OK) break;
         mftb200_ctx::Step prog_step([](mftb200_ctx* cc, cudaStream_t st) -> const char* {
             cc->launches++;
-            return conv_prog_launch(&cc->prog, cc->cur_pairs, 0, st);
+            return conv_prog_launch(&cc->prog_full, cc->cur_pairs, 0, cc->iters, st);
         }, 0);
-        prog_step.tag = 200;                                     // the iteration program
+        prog_step.tag = 201;
         r = run_one(c, prog_step);
+    } else if (!layered && c->prog_ok) {
+        // per iteration: the lookup kernel (needs the whole GPU's thread parallelism), then ONE persistent launch for the
+        // iteration's 11 convolutions
+        for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) {
+            c->cur_group = 0; c->cur_b0 = 0; c->cur_pairs = n_pairs;
+            r = run_one(c, c->iter_steps[0]);
+            if (r != MFTB200_OK) break;
+            mftb200_ctx::Step prog_step([](mftb200_ctx* cc, cudaStream_t st) -> const char* {
+                cc->launches++;
+                return conv_prog_launch(&cc->prog, cc->cur_pairs, 0, 1, st);
+            }, 0);
+            prog_step.tag = 200;
+            r = run_one(c, prog_step);
+        }
+    } else {
+        for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) r = run_steps_groups(c, c->iter_steps, groups, n_groups);
     }
     if (r == MFTB200_OK) r = run_steps_groups(c, c->final_steps, groups, n_groups);
     if (n_groups == 2) {
@@ -817,7 +841,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "conv_impl") == 0) { c->conv_impl = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
-    if (strcmp(key, "persist") == 0) { c->persist = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "persist") == 0 && value >= 0 && value <= 2) { c->persist = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }

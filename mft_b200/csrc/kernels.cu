@@ -2,6 +2,7 @@
 // selection / lookup arithmetic follows a defined fp32 operation order (one rounding per
 // operation, no contraction) so that results are bit-identical to oracle/mft_oracle.py.
 #include "kernels.h"
+#include "lookup.cuh"
 
 #include <cmath>
 
@@ -413,102 +414,21 @@ void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long row
 // pyramid lookup (core/corr.py:30-51) + flow operands of the motion encoder
 // one warp per (pair, source pixel)
 // ==========================================================================================
-// Per level the 81 sample points of a pixel are the 9x9 integer offsets of ONE position, so they share its
-// fractional part and a 10x10 integer neighbourhood of the pixel's correlation row.  The warp evaluates the
-// position once per level (the oracle's round trip on the first sample; the other samples' own round trips
-// differ from "first sample + k" by ~1e-6 px, four orders of magnitude below the fp16 rounding of the output),
-// stages the four neighbourhoods in shared memory (400 loads per pixel instead of 4 x 324) and blends.
-constexpr int kLkWin = 10;
-
+// The per-pixel routine lives in lookup.cuh (shared with the persistent refinement kernel, which runs the same lookup
+// as tiles of its dataflow program): one warp per (pair, source pixel) here.
 __global__ void __launch_bounds__(256)
 lookup_kernel(const LookupArgs a) {
     pdl_enter();
-    __shared__ float win[8][4][kLkWin * kLkWin + 4];
+    __shared__ float win[8][kLkWinFloats];
     const int npx = a.h * a.w;
     const int wib = threadIdx.x >> 5;
     const long pp = static_cast<long>(blockIdx.x) * 8 + wib;
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
     const int lane = threadIdx.x & 31;
-    const int n = static_cast<int>(pp % npx);
-    const int y = n / a.w, x = n % a.w;
-    const float cx = a.coords1[pp * 2], cy = a.coords1[pp * 2 + 1];
-    __half* out = a.corr16 + pp * 328;
-    const bool finite = isfinite(cx) && isfinite(cy);
-
-    // level-independent index maps of this lane: window elements e = lane + 32k, outputs o = lane + 32k
-    int ewy[4], ewx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int e = lane + 32 * k;
-        ewy[k] = e / kLkWin;
-        ewx[k] = e - ewy[k] * kLkWin;
-    }
-    int ooff[3];        // window offset of output o: x offset index i = o / 9 (columns), y offset index j = o % 9 (rows)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int o = lane + 32 * k;
-        const int i = o / 9, j = o - i * 9;
-        ooff[k] = j * kLkWin + i;
-    }
-    float wE[4], wS[4];
-    {
-        int hl = a.h, wl = a.w;
-        float div = 1.0f;
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const float px = roundtrip_div(cx / div - 4.0f, static_cast<float>(wl - 1));
-            const float py = roundtrip_div(cy / div - 4.0f, static_cast<float>(hl - 1));
-            const float fx = floorf(px), fy = floorf(py);
-            wE[l] = px - fx;
-            wS[l] = py - fy;
-            const int X0 = finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(wl + 16))) : 0;
-            const int Y0 = finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(hl + 16))) : 0;
-            const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (lane + 32 * k < kLkWin * kLkWin) {
-                    const int gx = X0 + ewx[k], gy = Y0 + ewy[k];
-                    win[wib][l][lane + 32 * k] = (finite && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
-                                                     ? __ldg(base + static_cast<long>(gy) * wl + gx) : 0.0f;
-                }
-            }
-            hl >>= 1; wl >>= 1; div *= 2.0f;
-        }
-    }
+    LookupPixel px;
+    lookup_gather(a, pp, lane, win[wib], px);
     __syncwarp();
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const float* W = win[wib][l];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (lane + 32 * k < 81) {
-                const float* q = W + ooff[k];
-                const float vnw = q[0], vne = q[1], vsw = q[kLkWin], vse = q[kLkWin + 1];
-                const float top = fmaf(wE[l], vne - vnw, vnw), bot = fmaf(wE[l], vse - vsw, vsw);
-                const float r = finite ? fmaf(wS[l], bot - top, top) : NAN;
-                out[l * 81 + lane + 32 * k] = __float2half_rn(r);
-            }
-        }
-    }
-    if (lane < 4) out[324 + lane] = __float2half_rn(0.0f);
-    // flow = coords1 - coords0 (core/raft.py:179); 7x7x2 zero-padded neighbourhood for convf1
-    const long pbase = pp - n;
-    __half* fp = a.flowpatch16 + pp * 104;
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-        const int k = lane + 32 * k4;
-        if (k < 104) {
-            float v = 0.0f;
-            if (k < 98) {
-                const int c = k & 1, t = k >> 1, ky = t / 7, kx = t - ky * 7;
-                const int yy = y + ky - 3, xx = x + kx - 3;
-                if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
-                    v = a.coords1[(pbase + static_cast<long>(yy) * a.w + xx) * 2 + c] - static_cast<float>(c == 0 ? xx : yy);
-            }
-            fp[k] = __float2half_rn(v);
-        }
-    }
-    if (lane < 2) a.X[pp * 512 + 382 + lane] = __float2half_rn((lane == 0 ? cx : cy) - static_cast<float>(lane == 0 ? x : y));
+    lookup_emit(a, pp, lane, win[wib], px);
 }
 
 void launch_lookup(const LookupArgs& a, cudaStream_t stream) {

@@ -174,14 +174,16 @@ def test_persistent_program_bit_identical(geom, seeded_weights):
     eng.set_option('persist', 0)
     ref = eng.refine(lefts, rights).clone()
     ref1 = eng.refine(lefts[:1], rights[:1]).clone()
-    eng.set_option('persist', 1)
-    for rep in range(3):
-        got = eng.refine(lefts, rights).clone()
-        eng.check_device()
-        assert torch.equal(ref, got), (geom, rep, (ref - got).abs().max().item())
-        got1 = eng.refine(lefts[:1], rights[:1]).clone()
-        eng.check_device()
-        assert torch.equal(ref1, got1), (geom, rep)
+    # 1 = one launch per iteration; 2 = all iterations + the pyramid lookup as tiles of ONE launch (iterations overlap)
+    for mode in (1, 2):
+        eng.set_option('persist', mode)
+        for rep in range(3 if mode == 1 else 2):
+            got = eng.refine(lefts, rights).clone()
+            eng.check_device()
+            assert torch.equal(ref, got), (geom, mode, rep, (ref - got).abs().max().item())
+            got1 = eng.refine(lefts[:1], rights[:1]).clone()
+            eng.check_device()
+            assert torch.equal(ref1, got1), (geom, mode, rep)
 
 
 def test_tracker_vs_oracle_real_128(real_weights):

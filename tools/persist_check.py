@@ -43,6 +43,13 @@ print(f'persist vs layered: bit-identical={bool(torch.equal(res[0], res[1]))} ma
       f'flow mean|diff|={d[:, :2].mean().item():.3e}')
 
 eng.set_option('persist', 1)
+import ctypes
+torch.cuda.synchronize()
+z = torch.zeros(8192, dtype=torch.int64, device='cuda')
+from mft_b200 import _lib
+ptr = ctypes.c_void_p(); nb = ctypes.c_size_t()
+_lib.check(_lib.lib().mftb200_debug_buffer(eng.ctx, b'prog_timing', ctypes.byref(ptr), ctypes.byref(nb)), eng.ctx)
+ctypes.cdll.LoadLibrary('libcudart.so').cudaMemset(ptr, 0, 65536)
 out = eng.refine(lefts, rights)
 t = eng.debug_buffer('prog_timing', torch.int64, (512, 16)).cpu().numpy().astype(float)
 t = t[t[:, 4] > 0]
@@ -51,5 +58,4 @@ print(f'{len(t)} CTAs; MMA warp: {us(t[:, 0].mean()):.1f} us in the launch, {t[:
 print(f'   MMA warp waits: ticket {us(t[:, 1].mean()):.1f} us, accumulator free {us(t[:, 2].mean()):.1f} us, '
       f'operands {us(t[:, 3].mean()):.1f} us ({t[:, 3].sum() / t[:, 5].sum():.0f} cycles per stage); '
       f'issue+rest {us((t[:, 0] - t[:, 1] - t[:, 2] - t[:, 3]).mean()):.1f} us')
-print(f'   epilogue warp 4: ticket {us(t[:, 8].mean()):.1f} us, accumulator ready {us(t[:, 9].mean()):.1f} us, '
-      f'epilogue {us(t[:, 10].mean()):.1f} us ({t[:, 10].sum() / t[:, 4].sum():.0f} cycles per tile), publish {us(t[:, 11].mean()):.1f} us')
+print(f'   lookup tiles: {t[:, 9].mean():.1f} per CTA, {us(t[:, 8].sum() / max(t[:, 9].sum(), 1)):.1f} us each (epilogue warp 4)')
