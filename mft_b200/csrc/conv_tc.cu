@@ -498,20 +498,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // convolution epilogues' (a spill costs an L2 round trip here -- the L1 is carved out for shared memory).
 __device__ __noinline__ void prog_lookup_tile(const LookupArgs& lk, const ConvGeom& g, float* win, int ew, int lane, int tx,
                                               int ty, int b) {
+    const LookupLane t = lookup_lane_init(lane);
     for (int r = 0; r < 16; r += 2) {
         long pp[2];
+        int xs[2], ys[2];
         LookupPixel px[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int row = ew * 16 + r + u;
             const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & (g.tile_w - 1));
+            xs[u] = x; ys[u] = y;
             pp[u] = (y < g.H && x < g.W) ? (static_cast<long>(b) * g.H + y) * g.W + x : -1;
-            if (pp[u] >= 0) lookup_gather(lk, pp[u], lane, win + u * kLkWinFloats, px[u]);
+            if (pp[u] >= 0) lookup_gather(lk, t, pp[u], lane, win + u * kLkWinFloats, px[u]);
         }
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-            if (pp[u] >= 0) lookup_emit(lk, pp[u], lane, win + u * kLkWinFloats, px[u]);
+            if (pp[u] >= 0) lookup_emit(lk, t, pp[u], xs[u], ys[u], lane, win + u * kLkWinFloats, px[u]);
         __syncwarp();
     }
 }

@@ -414,26 +414,42 @@ void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long row
 // pyramid lookup (core/corr.py:30-51) + flow operands of the motion encoder
 // one warp per (pair, source pixel)
 // ==========================================================================================
-// The per-pixel routine lives in lookup.cuh (shared with the persistent refinement kernel, which runs the same lookup
-// as tiles of its dataflow program): one warp per (pair, source pixel) here.
-__global__ void __launch_bounds__(256)
+// The per-pixel routine lives in lookup.cuh (shared with the persistent refinement kernel, which can run the same lookup
+// as tiles of its dataflow program).  Here: one warp per kLkPixPerWarp consecutive (pair, source pixel)s whose windows
+// are requested together (the kernel is latency bound: more loads in flight per warp, lane tables set up once).
+constexpr int kLkPixPerWarp = 1;
+
+__global__ void __launch_bounds__(256, 8)      // 32 registers: all 64 warps of the SM resident (the kernel is latency bound)
 lookup_kernel(const LookupArgs a) {
     pdl_enter();
-    __shared__ float win[8][kLkWinFloats];
+    __shared__ float win[8][kLkPixPerWarp][kLkWinFloats];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
+    const long p0 = (static_cast<long>(blockIdx.x) * 8 + wib) * kLkPixPerWarp;
+    if (p0 >= total) return;
+    const LookupLane t = lookup_lane_init(lane);
     const int npx = a.h * a.w;
-    const int wib = threadIdx.x >> 5;
-    const long pp = static_cast<long>(blockIdx.x) * 8 + wib;
-    if (pp >= static_cast<long>(a.n_pairs) * npx) return;
-    const int lane = threadIdx.x & 31;
-    LookupPixel px;
-    lookup_gather(a, pp, lane, win[wib], px);
+    const int n0 = static_cast<int>(p0 % npx);
+    LookupPixel px[kLkPixPerWarp];
+#pragma unroll
+    for (int i = 0; i < kLkPixPerWarp; ++i)
+        if (p0 + i < total) lookup_gather(a, t, p0 + i, lane, win[wib][i], px[i]);
     __syncwarp();
-    lookup_emit(a, pp, lane, win[wib], px);
+#pragma unroll
+    for (int i = 0; i < kLkPixPerWarp; ++i) {
+        if (p0 + i < total) {
+            int n = n0 + i;
+            if (n >= npx) n -= npx;              // first pixel of the next pair
+            const int y = n / a.w;
+            lookup_emit(a, t, p0 + i, n - y * a.w, y, lane, win[wib][i], px[i]);
+        }
+    }
 }
 
 void launch_lookup(const LookupArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
+    const long per_block = 8 * kLkPixPerWarp;
+    launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + per_block - 1) / per_block)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================

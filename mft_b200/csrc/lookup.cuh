@@ -1,5 +1,5 @@
 // Correlation-pyramid lookup of ONE source pixel by ONE warp (core/corr.py:30-51) + the flow operands of the motion
-// encoder.  Shared by lookup_kernel (kernels.cu) and by the persistent refinement kernel (conv_tc.cu), which runs the
+// encoder.  Shared by lookup_kernel (kernels.cu) and by the persistent refinement kernel (conv_tc.cu), which can run the
 // lookup as tiles of its dataflow program; both must produce the same bits, so the arithmetic below only uses
 // operations the compiler cannot contract differently in the two translation units (explicit fmaf, no a*b+c).
 //
@@ -8,6 +8,10 @@
 // level (the oracle's round trip on the first sample; the other samples' own round trips differ from "first sample
 // + k" by ~1e-6 px, four orders of magnitude below the fp16 rounding of the output), stages the four neighbourhoods in
 // shared memory (400 loads per pixel instead of 4 x 324) and blends.
+//
+// The kernel is instruction-issue bound (about 1300 instructions per lane and pixel in its first form), so everything
+// that only depends on the lane -- which window elements it fetches, which outputs it blends, which entries of the
+// 7x7 flow patch it writes -- is tabulated once per warp (LookupLane) and reused for every pixel the warp handles.
 #pragma once
 #include "kernels.h"
 
@@ -23,84 +27,112 @@ struct LookupPixel {
     bool finite;
 };
 
-// bilinear_sampler's normalise -> grid_sample(align_corners=True) round trip (core/utils/utils.py:98-106)
+// Per-lane constants.  Window element e = lane + 32k (k < 4, e < 100) sits at (ey, ex); output o = lane + 32k (k < 3,
+// o < 81) blends the 2x2 window cell at woff = (o % 9) * 10 + o / 9 (x offset index o / 9 = columns, core/corr.py:37-40);
+// flow-patch entry f = lane + 32k (k < 4, f < 98): channel f & 1 of tap (f >> 1) = ky * 7 + kx.
+struct LookupLane {
+    int ex[4], ey[4];
+    int woff[3];
+    int fdx[4], fdy[4];
+};
+
+__device__ __forceinline__ LookupLane lookup_lane_init(int lane) {
+    LookupLane t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        t.ey[k] = e / kLkWin;
+        t.ex[k] = e - t.ey[k] * kLkWin;
+        const int f = lane + 32 * k, tap = f >> 1;
+        t.fdy[k] = tap / 7 - 3;
+        t.fdx[k] = tap - (tap / 7) * 7 - 3;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int o = lane + 32 * k;
+        const int i = o / 9, j = o - i * 9;
+        t.woff[k] = j * kLkWin + i;
+    }
+    return t;
+}
+
+// bilinear_sampler's normalise -> grid_sample(align_corners=True) round trip (core/utils/utils.py:98-106).  The quotient
+// uses the 2-ulp fast division: the round trip itself only perturbs the position by ~1e-6 px, far below what the fp16
+// output resolves.
 __device__ __forceinline__ float lk_roundtrip_div(float c, float size_m1) {
-    const float g = (2.0f * c) / size_m1 - 1.0f;
+    const float g = __fadd_rn(__fdividef(2.0f * c, size_m1), -1.0f);      // (no contraction: same bits in every translation unit)
     return ((g + 1.0f) * 0.5f) * size_m1;
 }
 
 // Phase 1: request the four 10x10 windows of pixel `pp` (= pair * h*w + n) into `win` (this warp's kLkWinFloats floats).
 // coords1 may have been written earlier in the same launch by another CTA: read through L2.
-__device__ __forceinline__ void lookup_gather(const LookupArgs& a, long pp, int lane, float* win, LookupPixel& px) {
+__device__ __forceinline__ void lookup_gather(const LookupArgs& a, const LookupLane& t, long pp, int lane, float* win,
+                                              LookupPixel& px) {
     const float2 c = __ldcg(reinterpret_cast<const float2*>(a.coords1 + pp * 2));
     px.cx = c.x;
     px.cy = c.y;
     px.finite = isfinite(c.x) && isfinite(c.y);
     int hl = a.h, wl = a.w;
-    float div = 1.0f;
+    float inv = 1.0f;                                   // 1 / 2^level: the division by 2^level is exact either way
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        const float fxp = lk_roundtrip_div(c.x / div - 4.0f, static_cast<float>(wl - 1));
-        const float fyp = lk_roundtrip_div(c.y / div - 4.0f, static_cast<float>(hl - 1));
+        const float fxp = lk_roundtrip_div(c.x * inv - 4.0f, static_cast<float>(wl - 1));
+        const float fyp = lk_roundtrip_div(c.y * inv - 4.0f, static_cast<float>(hl - 1));
         const float fx = floorf(fxp), fy = floorf(fyp);
         px.wE[l] = fxp - fx;
         px.wS[l] = fyp - fy;
-        const int X0 = px.finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(wl + 16))) : 0;
-        const int Y0 = px.finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(hl + 16))) : 0;
-        const float* base = a.lvl[l] + pp * static_cast<long>(hl) * wl;
+        // non-finite coordinates: park the window outside the map, every tap then reads as zero (the output is NaN anyway)
+        const int X0 = px.finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(wl + 16))) : -64;
+        const int Y0 = px.finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(hl + 16))) : -64;
+        const float* base = a.lvl[l] + pp * static_cast<long>(hl * wl);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int e = lane + 32 * k;
-            if (e < kLkWin * kLkWin) {
-                const int ey = e / kLkWin, ex = e - ey * kLkWin;
-                const int gx = X0 + ex, gy = Y0 + ey;
-                win[l * kLkLevelFloats + e] = (px.finite && gx >= 0 && gx < wl && gy >= 0 && gy < hl)
-                                                  ? __ldg(base + static_cast<long>(gy) * wl + gx) : 0.0f;
+            if (k < 3 || lane < kLkWin * kLkWin - 96) {
+                const unsigned gx = static_cast<unsigned>(X0 + t.ex[k]), gy = static_cast<unsigned>(Y0 + t.ey[k]);
+                float v = 0.0f;
+                if (gx < static_cast<unsigned>(wl) && gy < static_cast<unsigned>(hl)) v = __ldg(base + gy * wl + gx);
+                win[l * kLkLevelFloats + lane + 32 * k] = v;
             }
         }
-        hl >>= 1; wl >>= 1; div *= 2.0f;
+        hl >>= 1; wl >>= 1; inv *= 0.5f;
     }
 }
 
 // Phase 2 (after a __syncwarp): blend, write corr16 [324 + 4 pad], the 7x7x2 flow neighbourhood for convf1 and the flow
 // channels of the GRU record.
-__device__ __forceinline__ void lookup_emit(const LookupArgs& a, long pp, int lane, const float* win, const LookupPixel& px) {
-    const int npx = a.h * a.w;
-    const int n = static_cast<int>(pp % npx);
-    const int y = n / a.w, x = n - y * a.w;
-    __half* out = a.corr16 + pp * 328;
+// (x, y) = the pixel's position in its frame (pp = pair * h*w + y*w + x).
+__device__ __forceinline__ void lookup_emit(const LookupArgs& a, const LookupLane& t, long pp, int x, int y, int lane,
+                                            const float* win, const LookupPixel& px) {
+    const int n = y * a.w + x;
+    __half* out = a.corr16 + pp * 328 + lane;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const float* W = win + l * kLkLevelFloats;
+        const float wE = px.wE[l], wS = px.wS[l];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const int o = lane + 32 * k;
-            if (o < 81) {
-                const int i = o / 9, j = o - i * 9;          // x offset index i (columns), y offset index j (rows)
-                const float* q = W + j * kLkWin + i;
+            if (k < 2 || lane < 81 - 64) {
+                const float* q = W + t.woff[k];
                 const float vnw = q[0], vne = q[1], vsw = q[kLkWin], vse = q[kLkWin + 1];
-                const float top = fmaf(px.wE[l], vne - vnw, vnw), bot = fmaf(px.wE[l], vse - vsw, vsw);
-                const float r = px.finite ? fmaf(px.wS[l], bot - top, top) : NAN;
-                out[l * 81 + o] = __float2half_rn(r);
+                const float top = fmaf(wE, vne - vnw, vnw), bot = fmaf(wE, vse - vsw, vsw);
+                const float r = px.finite ? fmaf(wS, bot - top, top) : NAN;
+                out[l * 81 + 32 * k] = __float2half_rn(r);
             }
         }
     }
-    if (lane < 4) out[324 + lane] = __float2half_rn(0.0f);
+    if (lane < 4) out[324] = __float2half_rn(0.0f);
     // flow = coords1 - coords0 (core/raft.py:179); 7x7x2 zero-padded neighbourhood for convf1
-    const long pbase = pp - n;
-    __half* fp = a.flowpatch16 + pp * 104;
+    const float* cbase = a.coords1 + (pp - n) * 2;
+    __half* fp = a.flowpatch16 + pp * 104 + lane;
+    const int ch = lane & 1;
 #pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-        const int k = lane + 32 * k4;
-        if (k < 104) {
+    for (int k = 0; k < 4; ++k) {
+        if (k < 3 || lane < 104 - 96) {
             float v = 0.0f;
-            if (k < 98) {
-                const int c = k & 1, t = k >> 1, ky = t / 7, kx = t - ky * 7;
-                const int yy = y + ky - 3, xx = x + kx - 3;
-                if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
-                    v = __ldcg(a.coords1 + (pbase + static_cast<long>(yy) * a.w + xx) * 2 + c) - static_cast<float>(c == 0 ? xx : yy);
-            }
-            fp[k] = __float2half_rn(v);
+            const unsigned xx = static_cast<unsigned>(x + t.fdx[k]), yy = static_cast<unsigned>(y + t.fdy[k]);
+            if ((k < 3 || lane < 98 - 96) && xx < static_cast<unsigned>(a.w) && yy < static_cast<unsigned>(a.h))
+                v = __ldcg(cbase + (yy * a.w + xx) * 2 + ch) - static_cast<float>(ch == 0 ? xx : yy);
+            fp[32 * k] = __float2half_rn(v);
         }
     }
     if (lane < 2) a.X[pp * 512 + 382 + lane] = __float2half_rn((lane == 0 ? px.cx : px.cy) - static_cast<float>(lane == 0 ? x : y));
