@@ -633,24 +633,24 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                 prog_decode(P, item, it, l, b, tile);
                 const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
                 const ProgLayer& L = P.L[l];
-                if (lane < 18) {
-                    const int sl = lane < 9 ? L.succ0 : L.succ1;
-                    const int j = lane < 9 ? lane : lane - 9;
-                    const int nty = ty + j / 3 - 1, ntx = tx + j % 3 - 1;
-                    if (sl >= 0 && nty >= 0 && nty < P.tiles_y && ntx >= 0 && ntx < P.tiles_x) {
-                        // the successor tile of iteration `its` is ready when all (its - shift + 1) rounds of arrivals are in
-                        // (a round = every predecessor layer x every tile of the 3x3 neighbourhood); rounds cannot mix because
-                        // round r+1 only starts arriving after the tile itself has run in round r (it is their ancestor)
-                        const ProgLayer& S = P.L[sl];
-                        const int its = it + S.iter_shift;
-                        if (its < P.iters) {
-                            const int nn = (1 + (ntx > 0) + (ntx < P.tiles_x - 1)) * (1 + (nty > 0) + (nty < P.tiles_y - 1));
-                            const int nt = nty * P.tiles_x + ntx;
-                            const int old = atom_add_acq_rel_gpu(arr_cur + (static_cast<long>(sl * P.max_batch + b) * tpp + nt), 1);
-                            if (old + 1 == (it + 1) * S.n_dep * nn)
-                                push(static_cast<uint32_t>(((its * P.n_layers + sl) * P.nbatch + (b - P.b0)) * tpp + nt));
-                        }
-                    }
+#pragma unroll
+                for (int si = 0; si < 2; ++si) {            // one pass per successor layer, one lane per tile of its 5x5 reach
+                    const int sl = si == 0 ? L.succ0 : L.succ1;
+                    if (sl < 0 || lane >= 25) continue;
+                    const ProgLayer& S = P.L[sl];
+                    const int dy = lane / 5 - 2, dx = lane - (lane / 5) * 5 - 2;
+                    const int nty = ty + dy, ntx = tx + dx;
+                    if (abs(dy) > S.ry || abs(dx) > S.rx || nty < 0 || nty >= P.tiles_y || ntx < 0 || ntx >= P.tiles_x) continue;
+                    // the successor tile of iteration `its` is ready when all (its - shift + 1) rounds of arrivals are in
+                    // (a round = every predecessor layer x every tile within the dependency radius); rounds cannot mix because
+                    // round r+1 only starts arriving after the tile itself has run in round r (it is their ancestor)
+                    const int its = it + S.iter_shift;
+                    if (its >= P.iters) continue;
+                    const int nn = (1 + min(S.rx, ntx) + min(S.rx, P.tiles_x - 1 - ntx)) * (1 + min(S.ry, nty) + min(S.ry, P.tiles_y - 1 - nty));
+                    const int nt = nty * P.tiles_x + ntx;
+                    const int old = atom_add_acq_rel_gpu(arr_cur + (static_cast<long>(sl * P.max_batch + b) * tpp + nt), 1);
+                    if (old + 1 == (it + 1) * S.n_dep * nn)
+                        push(static_cast<uint32_t>(((its * P.n_layers + sl) * P.nbatch + (b - P.b0)) * tpp + nt));
                 }
                 __syncwarp();
                 if (lane == 0) ctl->stored[slot] = 0;
@@ -1374,7 +1374,7 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
 // ------------------------------------------------------------------------------------------
 // layer programs (host side)
 // ------------------------------------------------------------------------------------------
-const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1) {
+const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1, bool exact_halo) {
     if (prog->n_layers >= kMaxProgLayers) return "conv_prog_add: too many layers";
     const ConvGeom& g = p.g;
     if (p.variant != 1 || g.cluster != 1 || g.n_tiles != 1) return "conv_prog_add: layer needs the plain 128-pixel kernel, one cout tile";
@@ -1393,6 +1393,13 @@ const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int de
     L.n_dep = (dep0 >= 0) + (dep1 >= 0);
     L.kind = 0;
     L.iter_shift = 0;
+    // dependency radius in tiles = the window's reach in pixels over the tile size (at least the 3x3 neighbourhood when
+    // iterations overlap inside one launch); the scheduler enumerates a 5x5 reach at most
+    L.ry = (g.kh / 2 + g.tile_h - 1) / g.tile_h;
+    L.rx = (g.kw / 2 + g.tile_w - 1) / g.tile_w;
+    if (!exact_halo) { L.ry = L.ry > 1 ? L.ry : 1; L.rx = L.rx > 1 ? L.rx : 1; }
+    if (L.ry > 2 || L.rx > 2) { --prog->n_layers; return "conv_prog_add: tile too small for this layer's halo"; }
+    L.pad_[0] = L.pad_[1] = 0;
     L.g.b0 = 0;
     return nullptr;
 }
@@ -1416,6 +1423,9 @@ const char* conv_prog_add_lookup(ConvProgram* prog, const ConvPlan& like, const 
     L.n_dep = 1;
     L.kind = 1;
     L.iter_shift = 1;
+    L.ry = (3 + g.tile_h - 1) / g.tile_h;      // the 7x7 flow patch reaches 3 pixels into the neighbouring tiles
+    L.rx = (3 + g.tile_w - 1) / g.tile_w;
+    if (L.ry > 2 || L.rx > 2) return "conv_prog_add_lookup: tile too small for the lookup's halo";
     prog->lk = lk;
     return nullptr;
 }

@@ -143,6 +143,7 @@ namespace {
 struct Builder {
     mftb200_ctx* c;
     const char* err = nullptr;
+    int def_th = 0, def_tw = 0;          // tile forced on every plan that does not ask for one itself (0 = choose_tile)
 
     // Adds a conv plan; returns its index (or -1 and sets err).
     int conv(int layer, Act in, int batch, int stride, TapList taps, int n_tile, int mode, int force_th = 0,
@@ -152,6 +153,7 @@ struct Builder {
         const LayerW* L = layer >= 0 ? &c->layers[layer] : nullptr;
         const __half* wt = L ? L->w : bmat;
         const int cout_pad = L ? L->cout_pad : cout;
+        if (force_th == 0 && stride == 1) { force_th = def_th; force_tw = def_tw; }
         const char* e = conv_plan_init(&p, in.base, in.pitch, in.C, in.H, in.W, batch, stride, taps, wt, cout_pad,
                                        n_tile, b_rows, force_th, force_tw);
         if (e) { err = e; return -1; }
@@ -327,6 +329,10 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     });
 
     // ---- one GRU iteration (core/raft.py:173-184, core/update.py:229-238) ------------------
+    // Full-width tiles when the coarse map is a power of two wide (64x64 at 512^2: tiles of 2 rows x 64): the 1x5 GRU
+    // convolutions then have no halo in another tile at all and the 3x3 / 5x1 ones only in the tiles above / below, so a
+    // tile of the dataflow program waits for 1 or 3 predecessor tiles instead of 9.
+    if (w <= 128 && (w & (w - 1)) == 0) { B.def_tw = w; B.def_th = 128 / w; }
     auto& S = c->iter_steps;
     S.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
@@ -417,15 +423,16 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         };
         memset(&c->prog, 0, sizeof c->prog);
         const char* pe = nullptr;
-        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], depsA[k][0], depsA[k][1]);
+        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], depsA[k][0], depsA[k][1], true);
         if (!pe) c->prog_ok = finish(c->prog, 1);
         memset(&c->prog_full, 0, sizeof c->prog_full);
         LookupArgs lk{{c->corr[0], c->corr[1], c->corr[2], c->corr[3]}, c->coords1, c->corr16, c->flowpatch, c->X, mp, h, w};
         pe = conv_prog_add_lookup(&c->prog_full, c->plans[pi[0]], lk, 11);
-        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog_full, c->plans[pi[k]], depsB[k][0], depsB[k][1]);
+        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog_full, c->plans[pi[k]], depsB[k][0], depsB[k][1], false);
         if (!pe) c->prog_full_ok = finish(c->prog_full, 64);
     }
 
+    B.def_th = B.def_tw = 0;
     // ---- after the last iteration: mask head || OU head (independent until the upsampling), convex upsampling --------
     auto& Fz = c->final_steps;
     Act a_ou1{c->c1buf, 256, 256, h, w};       // the OU branch keeps its hidden layer in c1buf (free after the last iteration)
