@@ -85,6 +85,15 @@ int mftb200_warp_backward(const float* flow, const float* img, int C, int H, int
 int mftb200_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
                           float* out, mftb200_stream stream);
 
+/* Forward splat == FlowOUTrackingResult.warp_forward -> interpolation.bilinear_splat (MFT/results.py:190-248,
+ * MFT/utils/interpolation.py:234-309; demo.py:139-144 propagates an edit with it): img (H,W,C) float is splatted to
+ * grid + flow with the reference's clamped bilinear weights and normalised by the accumulated weight; cells that
+ * receive nothing stay 0, or `border` when use_border != 0.  mask: (H,W) uint8 (0 = skip the source pixel) or NULL.
+ * out: (H,W,C); counts: (H,W) float scratch (returns the accumulated weights).  Float atomics: equal to the
+ * reference up to summation order. */
+int mftb200_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
+                         float border, float* out, float* counts, mftb200_stream stream);
+
 /* ---- diagnostics / test hooks ---------------------------------------------------------------- */
 int mftb200_device_error_flag(mftb200_ctx* ctx);          /* syncs; 0 = clean */
 /* keys: "conv_impl" 0 = tcgen05 (product), 1 = SIMT cross-check kernel (tests only); "iters" = GRU

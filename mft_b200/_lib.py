@@ -32,6 +32,7 @@ def _declare(lib):
         'mftb200_chain_select': (ci, [ci, C.POINTER(vp), vp, cf, ci, ci, vp, vp, vp]),
         'mftb200_warp_backward': (ci, [vp, vp, ci, ci, ci, ci, vp, vp]),
         'mftb200_sample_points': (ci, [vp, ci, ci, ci, vp, ci, ci, vp, vp]),
+        'mftb200_warp_forward': (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, vp]),
         'mftb200_device_error_flag': (ci, [vp]),
         'mftb200_set_option': (ci, [vp, C.c_char_p, ci]),
         'mftb200_set_global_option': (ci, [C.c_char_p, ci]),

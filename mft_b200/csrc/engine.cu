@@ -830,6 +830,13 @@ int mftb200_sample_points(const float* field, int C, int H, int W, const float* 
     return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
 }
 
+int mftb200_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
+                         float border, float* out, float* counts, mftb200_stream stream) {
+    if (!flow || !img || !out || !counts || C < 1 || H < 1 || W < 1) return MFTB200_ERR_ARG;
+    launch_warp_forward(flow, img, mask, C, H, W, use_border, border, out, counts, static_cast<cudaStream_t>(stream));
+    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+}
+
 int mftb200_device_error_flag(mftb200_ctx* c) {
     if (!c) return MFTB200_ERR_ARG;
     int v = 0;

@@ -199,6 +199,57 @@ void launch_sample_points(const float* field, int C, int H, int W, const float* 
 }
 
 // ==========================================================================================
+// forward splat (MFT/results.py:190-248, MFT/utils/interpolation.py:234-309)
+// ==========================================================================================
+__global__ void __launch_bounds__(256)
+splat_scatter_kernel(const float* __restrict__ flow, const float* __restrict__ img, const uint8_t* __restrict__ mask, int C,
+                     int H, int W, float* __restrict__ accum, float* __restrict__ counts) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const long hw = static_cast<long>(H) * W, p = static_cast<long>(y) * W + x;
+    if (mask != nullptr && mask[p] == 0) return;
+    float px = static_cast<float>(x) + flow[p], py = static_cast<float>(y) + flow[hw + p];
+    if (!(isfinite(px) && isfinite(py))) return;
+    // corner indices from the UNCLAMPED floor, then position and corners clamped into the grid (interpolation.py:256-268)
+    const float fx0 = fminf(fmaxf(floorf(px), -2.0f), static_cast<float>(W + 1));
+    const float fy0 = fminf(fmaxf(floorf(py), -2.0f), static_cast<float>(H + 1));
+    int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0), x1 = x0 + 1, y1 = y0 + 1;
+    px = fminf(fmaxf(px, 0.0f), static_cast<float>(W - 1));
+    py = fminf(fmaxf(py, 0.0f), static_cast<float>(H - 1));
+    x0 = min(max(x0, 0), W - 1); x1 = min(max(x1, 0), W - 1);
+    y0 = min(max(y0, 0), H - 1); y1 = min(max(y1, 0), H - 1);
+    const float ax = static_cast<float>(x1) - px, bx = px - static_cast<float>(x0);
+    const float ay = static_cast<float>(y1) - py, by = py - static_cast<float>(y0);
+    const float w[4] = {ax * ay, ax * by, bx * ay, bx * by};
+    const long cell[4] = {static_cast<long>(y0) * W + x0, static_cast<long>(y1) * W + x0, static_cast<long>(y0) * W + x1,
+                          static_cast<long>(y1) * W + x1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (w[k] == 0.0f) continue;
+        atomicAdd(counts + cell[k], w[k]);
+        for (int c = 0; c < C; ++c) atomicAdd(accum + cell[k] * C + c, img[p * C + c] * w[k]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+splat_normalize_kernel(float* __restrict__ out, const float* __restrict__ counts, int C, long cells, int use_border, float border) {
+    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= cells * C) return;
+    const float n = counts[i / C];
+    out[i] = n > 0.0f ? out[i] / n : (use_border ? border : out[i]);
+}
+
+void launch_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
+                         float border, float* out, float* counts, cudaStream_t stream) {
+    const long cells = static_cast<long>(H) * W;
+    cudaMemsetAsync(out, 0, sizeof(float) * cells * C, stream);
+    cudaMemsetAsync(counts, 0, sizeof(float) * cells, stream);
+    splat_scatter_kernel<<<dim3((W + 255) / 256, H), 256, 0, stream>>>(flow, img, mask, C, H, W, out, counts);
+    splat_normalize_kernel<<<static_cast<unsigned>((cells * C + 255) / 256), 256, 0, stream>>>(out, counts, C, cells, use_border, border);
+}
+
+// ==========================================================================================
 // frame -> im2col patches for the 7x7/2 first conv (MFT/raft.py:41-48, core/raft.py:122-124)
 // ==========================================================================================
 __global__ void __launch_bounds__(256)

@@ -30,6 +30,14 @@ void launch_warp_backward(const float* flow, const float* img, int C, int H, int
 void launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
                           float* out, cudaStream_t stream);
 
+// Forward splat (FlowOUTrackingResult.warp_forward -> interpolation.bilinear_splat, MFT/results.py:190-248,
+// MFT/utils/interpolation.py:234-309): every (unmasked) source pixel adds img[y,x,:] * w to the four grid cells around
+// (x, y) + flow with the reference's clamped bilinear weights; out = accum / counts where counts > 0, else 0 (or `border`).
+// img / out: (H,W,C) float; mask: (H,W) uint8 or nullptr; counts: (H,W) float scratch.  Accumulation uses float atomics
+// (order is not defined: results agree with the oracle to rounding, not bit for bit).
+void launch_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
+                         float border, float* out, float* counts, cudaStream_t stream);
+
 // uint8 BGR HWC frame -> fp16 im2col patches of the encoders' 7x7 stride-2 first conv,
 // [ (Hp/2)*(Wp/2) ][152], k = (ky*7+kx)*3 + c (c: R,G,B), values 2*(v/255)-1; the frame is
 // replicate-padded to Hp x Wp (pad_left/pad_top) first, the conv itself zero-pads.

@@ -149,35 +149,56 @@ class FlowOUTrackingResult:
         s = self._sample_points(self.packed(), points, add_points=False)
         return s[0:2], s[2:3], s[3:4]
 
-    def warp_forward(self, img, mask=None, border=None):
-        """Forward-splat img (H,W,...) by self.flow with bilinear weights, normalised by the
-        accumulated weight (results.py:190-248 -> interpolation.bilinear_splat).  Caller-side
-        helper of demo.py's edit propagation; torch ops on whatever device the result lives on."""
+    def warp_forward(self, img, mask=None, border=None, numpy_out=True):
+        """Forward-splat img (H,W,...) by self.flow with the reference's clamped bilinear weights, normalised by the
+        accumulated weight (results.py:190-248 -> interpolation.bilinear_splat, interpolation.py:234-309; demo.py's edit
+        propagation).  On a CUDA result this is the library's splat kernel (float atomics); on a CPU result the same
+        arithmetic in torch ops (caller-side convenience, not the tracking path)."""
         dev = self.flow.device
         img_t = _as_f32(img, dev)
         H, W = self.H, self.W
         assert tuple(img_t.shape[:2]) == (H, W)
-        vals = img_t.reshape(H * W, -1)
-        ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing='ij')
-        pos = torch.stack([xs + self.flow[0], ys + self.flow[1]], -1).reshape(H * W, 2)
+        vals = img_t.reshape(H, W, -1).contiguous()
+        Cn = int(vals.shape[2])
+        m = None
         if mask is not None:
-            m = torch.as_tensor(np.asarray(mask) if not isinstance(mask, torch.Tensor) else mask, device=dev).reshape(-1).bool()
-            pos, vals = pos[m], vals[m]
-        accum = torch.zeros((H * W, vals.shape[1]), dtype=torch.float32, device=dev)
-        cnt = torch.zeros((H * W, 1), dtype=torch.float32, device=dev)
-        x0, y0 = torch.floor(pos[:, 0]), torch.floor(pos[:, 1])
-        for dx in (0, 1):
-            for dy in (0, 1):
-                xi, yi = x0 + dx, y0 + dy
-                wgt = (1 - (pos[:, 0] - xi).abs()) * (1 - (pos[:, 1] - yi).abs())
-                ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
-                lin = (yi.long() * W + xi.long())[ok]
-                accum.index_add_(0, lin, vals[ok] * wgt[ok, None])
-                cnt.index_add_(0, lin, wgt[ok, None])
-        out = torch.where(cnt > 0, accum / cnt.clamp_min(1e-20), accum)
-        if border is not None:
-            out = torch.where(cnt > 0, out, torch.full_like(out, float(border)))
-        return out.reshape(img_t.shape).cpu().numpy()
+            m = torch.as_tensor(np.asarray(mask) if not isinstance(mask, torch.Tensor) else mask, device=dev).reshape(H, W)
+        if self.flow.is_cuda:
+            flow = self.flow.float().contiguous()
+            out = torch.empty((H, W, Cn), dtype=torch.float32, device=dev)
+            cnt = torch.empty((H, W), dtype=torch.float32, device=dev)
+            m8 = m.to(torch.uint8).contiguous() if m is not None else None
+            _lib.check(_lib.lib().mftb200_warp_forward(C.c_void_p(flow.data_ptr()), C.c_void_p(vals.data_ptr()),
+                                                       C.c_void_p(m8.data_ptr() if m8 is not None else None), Cn, H, W,
+                                                       int(border is not None), float(border if border is not None else 0.0),
+                                                       C.c_void_p(out.data_ptr()), C.c_void_p(cnt.data_ptr()), _sptr()))
+        else:
+            ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+            x = (xs + self.flow[0].float()).reshape(-1)
+            y = (ys + self.flow[1].float()).reshape(-1)
+            v = vals.reshape(H * W, Cn)
+            if m is not None:
+                keep = m.reshape(-1).bool()
+                x, y, v = x[keep], y[keep], v[keep]
+            x0, y0 = torch.floor(x).long(), torch.floor(y).long()
+            x1, y1 = x0 + 1, y0 + 1
+            x, y = x.clamp(0, W - 1), y.clamp(0, H - 1)
+            x0, x1, y0, y1 = x0.clamp(0, W - 1), x1.clamp(0, W - 1), y0.clamp(0, H - 1), y1.clamp(0, H - 1)
+            acc = torch.zeros((H * W, Cn), dtype=torch.float32)
+            cnt = torch.zeros((H * W,), dtype=torch.float32)
+            for wgt, yy, xx in (((x1 - x) * (y1 - y), y0, x0), ((x1 - x) * (y - y0), y1, x0),
+                                ((x - x0) * (y1 - y), y0, x1), ((x - x0) * (y - y0), y1, x1)):
+                lin = yy * W + xx
+                acc.index_add_(0, lin, v * wgt[:, None])
+                cnt.index_add_(0, lin, wgt)
+            nz = cnt > 0
+            out = acc.clone()
+            out[nz] = out[nz] / cnt[nz][:, None]
+            if border is not None:
+                out[~nz] = float(border)
+            out = out.reshape(H, W, Cn)
+        out = out.reshape(img_t.shape)
+        return out.cpu().numpy() if numpy_out else out
 
     # ---- persistence ----------------------------------------------------------------------------
     def write(self, path):

@@ -12,6 +12,8 @@ Files
   raft_real_128.npz     same pairs with the shipped checkpoint (needs the checkpoint at test time)
   chain_select.npz      MFT.track's chaining + selection + invalid mask through the reference's own
                         tracker class around a replay flower (synthetic flows incl. overflow/ties/all-occluded/OOB)
+  warp_forward.npz      FlowOUTrackingResult.warp_forward (bilinear forward splat, results.py:190-248) of a random image
+                        through a random flow with end points outside the grid, with and without mask / border
   track_real_128.npz    10 demo frames at 128x128, deltas [inf,1,2,4,8], shipped checkpoint: the
                         reference tracker's per-frame results (full field for 3 frames + per-frame sums)
 """
@@ -45,6 +47,21 @@ def raft_pairs(model, frames, pairs, tag):
         out[f'sigma_{a}_{b}'] = _np(ex['sigma'])
         out[f'coords_{a}_{b}'] = _np(ex['raw']['coords'][0])
     return out
+
+
+def warp_forward_case():
+    R._import_reference()
+    from MFT.results import FlowOUTrackingResult as RefRes
+    rng = np.random.default_rng(77)
+    H, W = 40, 56
+    flow = (rng.standard_normal((2, H, W)) * 6).astype(np.float32)
+    flow[:, :4, :] += 30
+    flow[:, -3:, :] -= 40          # end points outside the grid on both sides
+    img = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    mask = rng.uniform(0, 1, (H, W)) > 0.3
+    res = RefRes(torch.from_numpy(flow), torch.zeros(1, H, W), torch.zeros(1, H, W))
+    return dict(flow=flow, img=img, mask=mask, out_plain=res.warp_forward(img).astype(np.float32),
+                out_mask=res.warp_forward(img, mask=mask, border=-1.0).astype(np.float32))
 
 
 def chain_select_case(rng, H, W, K, thr):
@@ -169,6 +186,7 @@ def main():
     g['ncase'] = np.array(ncase)
     g['thr'] = np.array(0.02, np.float32)
     np.savez_compressed(os.path.join(OUT, 'chain_select.npz'), **g)
+    np.savez_compressed(os.path.join(OUT, 'warp_forward.npz'), **warp_forward_case())
 
     # --- short real tracking run ---------------------------------------------------------------
     deltas = [np.inf, 1, 2, 4, 8]

@@ -580,3 +580,55 @@ class OracleTracker:
                 continue
             del self.memory[k]
         return SimpleNamespace(result=(flow, occ, sig), index=idx, live=live)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# forward splat: FlowOUTrackingResult.warp_forward -> interpolation.bilinear_splat
+# ------------------------------------------------------------------------------------------------------------------
+def bilinear_splat(data, coords, H, W):
+    """MFT/utils/interpolation.py:234-309.  data (N,C) float32, coords (N,2) xy float32 -> accum (H,W,C), counts (H,W).
+    Points are NOT dropped at the border: coordinates and the four corner indices are clamped into the grid (x1 is taken
+    from the unclamped floor, :256-268), which gives out-of-grid points zero weight on the clamped axis."""
+    data = np.asarray(data, np.float32)
+    x = np.asarray(coords[:, 0], np.float32)
+    y = np.asarray(coords[:, 1], np.float32)
+    x0 = np.floor(x).astype(np.int64)
+    y0 = np.floor(y).astype(np.int64)
+    x1, y1 = x0 + 1, y0 + 1
+    x = np.clip(x, 0, W - 1).astype(np.float32)
+    y = np.clip(y, 0, H - 1).astype(np.float32)
+    x0, x1 = np.clip(x0, 0, W - 1), np.clip(x1, 0, W - 1)
+    y0, y1 = np.clip(y0, 0, H - 1), np.clip(y1, 0, H - 1)
+    x0f, x1f, y0f, y1f = (v.astype(np.float32) for v in (x0, x1, y0, y1))
+    w_a = (x1f - x) * (y1f - y)
+    w_b = (x1f - x) * (y - y0f)
+    w_c = (x - x0f) * (y1f - y)
+    w_d = (x - x0f) * (y - y0f)
+    accum = np.zeros((H * W, data.shape[1]), np.float32)
+    counts = np.zeros((H * W,), np.float32)
+    for wgt, yy, xx in ((w_a, y0, x0), (w_b, y1, x0), (w_c, y0, x1), (w_d, y1, x1)):     # (:289-292 ordering)
+        lin = yy * W + xx
+        np.add.at(accum, lin, data * wgt[:, None])
+        np.add.at(counts, lin, wgt)
+    return accum.reshape(H, W, -1), counts.reshape(H, W)
+
+
+def warp_forward(flow, img, mask=None, border=None):
+    """MFT/results.py:190-248.  flow (2,H,W), img (H,W,C) -> (H,W,C): values splatted to grid + flow, normalised by the
+    accumulated weight where it is > 0; elsewhere 0 (or `border`)."""
+    flow = np.asarray(flow, np.float32)
+    H, W = flow.shape[1:]
+    img = np.asarray(img, np.float32).reshape(H, W, -1)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
+    pos = np.stack([xs + flow[0], ys + flow[1]], -1).reshape(-1, 2).astype(np.float32)
+    vals = img.reshape(H * W, -1)
+    if mask is not None:
+        m = np.asarray(mask).reshape(-1).astype(bool)
+        pos, vals = pos[m], vals[m]
+    accum, counts = bilinear_splat(vals, pos, H, W)
+    out = accum.copy()
+    nz = counts > 0
+    out[nz] /= counts[nz][:, None]
+    if border is not None:
+        out[~nz] = border
+    return out

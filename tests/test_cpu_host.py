@@ -203,7 +203,11 @@ def test_results_cpu_paths_match_oracle():
     pts = torch.tensor([[0.0, 0.0], [W - 1.0, H - 1.0], [3.5, 4.25]])
     assert torch.allclose(ident.warp_forward_points(pts), pts)
     img = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
-    assert np.abs(ident.warp_forward(img) - img).max() < 1e-6         # zero flow splats in place
+    # zero flow splats in place -- except the last row / column, which the reference's clamped corner indices give zero
+    # weight (interpolation.py:256-278: x0 == x1 == W-1 there)
+    wfz = ident.warp_forward(img)
+    assert np.abs(wfz[:-1, :-1] - img[:-1, :-1]).max() < 1e-6 and np.abs(wfz[-1]).max() == 0 and np.abs(wfz[:, -1]).max() == 0
+    assert np.abs(wfz - O.warp_forward(np.zeros((2, H, W), np.float32), img)).max() < 1e-6
 
 
 def _gloo_worker(rank, world, port, out):
@@ -278,3 +282,35 @@ def test_flow_cache_protocol_host_logic(monkeypatch):
     trk.init(img(0), flow_cache=cache)
     trk.track(img(1))
     assert (0, 1) in cache.store
+
+
+def test_warp_forward_cpu_path_matches_reference_golden():
+    """FlowOUTrackingResult.warp_forward on a CPU result (what demo.py holds) follows the reference's clamped splat."""
+    import numpy as np
+    import torch
+    from conftest import golden
+    from mft_b200.results import FlowOUTrackingResult
+    g = golden('warp_forward.npz')
+    r = FlowOUTrackingResult(torch.from_numpy(g['flow']))
+    assert np.abs(r.warp_forward(g['img']) - g['out_plain']).max() < 1e-6
+    assert np.abs(r.warp_forward(g['img'], mask=g['mask'], border=-1.0) - g['out_mask']).max() < 1e-6
+
+
+def test_device_flow_cache_protocol_on_cpu_tensors():
+    """read / write protocol of the reference FlowCache (io.py:655-698), LRU eviction under a byte budget, fp16 storage."""
+    import torch
+    from mft_b200.flow_cache import DeviceFlowCache
+    H, W = 8, 12
+    one = 4 * H * W * 4
+    c = DeviceFlowCache(max_bytes=3 * one, device='cpu')
+    assert c.read(0, 1) == (None, None, None)
+    for i in range(5):
+        c.write(i, i + 1, torch.full((2, H, W), float(i)), torch.zeros(1, H, W), torch.ones(1, H, W))
+    assert len(c) == 3 and c.evictions == 2 and c.read(0, 1)[0] is None
+    f, o, s = c.read(3, 4)
+    assert tuple(f.shape) == (2, H, W) and tuple(o.shape) == (1, H, W) and tuple(s.shape) == (1, H, W) and f.mean() == 3
+    c.write(9, 10, torch.zeros(2, H, W), torch.zeros(1, H, W), torch.ones(1, H, W))      # evicts (2,3): (3,4) was just used
+    assert c.read(2, 3)[0] is None and c.read(3, 4)[0] is not None
+    h = DeviceFlowCache(dtype=torch.float16, device='cpu')
+    h.write(0, 1, torch.full((2, H, W), 1.5), torch.zeros(1, H, W), torch.ones(1, H, W))
+    assert h.bytes == one // 2 and h.read(0, 1)[0].dtype == torch.float32 and h.read(0, 1)[0].mean() == 1.5

@@ -171,3 +171,30 @@ def test_conv_kernel_vs_torch(case, impl):
     _E().set_global_option('conv_v2', 0)
     err = (out[..., :cout] - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize('size', [(40, 56), (512, 512)])
+def test_warp_forward_splat_kernel(size):
+    """Forward splat kernel (mftb200_warp_forward) against the oracle restatement of the reference's bilinear_splat; at the
+    golden size also against the vectors recorded from the reference itself.  Float atomics: equal up to summation order."""
+    from mft_b200.results import FlowOUTrackingResult
+    H, W = size
+    if size == (40, 56):
+        g = golden('warp_forward.npz')
+        flow, img, mask = g['flow'], g['img'], g['mask']
+    else:
+        rng = np.random.default_rng(5)
+        flow = (rng.standard_normal((2, H, W)) * 8).astype(np.float32)
+        flow[:, :9] += 600.0
+        img = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+        mask = rng.uniform(0, 1, (H, W)) > 0.2
+    res = FlowOUTrackingResult(torch.from_numpy(flow).cuda())
+    got = res.warp_forward(img)
+    got_m = res.warp_forward(torch.from_numpy(img).cuda(), mask=mask, border=-1.0)
+    assert np.abs(got - O.warp_forward(flow, img)).max() < 2e-5
+    assert np.abs(got_m - O.warp_forward(flow, img, mask, -1.0)).max() < 2e-5
+    if size == (40, 56):
+        assert np.abs(got - g['out_plain']).max() < 2e-5 and np.abs(got_m - g['out_mask']).max() < 2e-5
+    # a zero flow splats every pixel onto itself (the reference gives the last row / column zero weight)
+    ident = FlowOUTrackingResult.identity((H, W), device='cuda')
+    assert np.abs(ident.warp_forward(img)[:-1, :-1] - img[:-1, :-1]).max() < 1e-6

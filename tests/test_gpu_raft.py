@@ -282,6 +282,16 @@ def test_backward_tracking_and_flow_cache(seeded_weights):
     for a, b in zip(*runs):
         assert torch.equal(a, b)
     assert all(torch.isfinite(a).all() for a in runs[0])
+    # the device-resident cache (mft_b200.flow_cache.DeviceFlowCache, fp32) must replay bit for bit as well
+    from mft_b200.flow_cache import DeviceFlowCache
+    dcache = DeviceFlowCache()
+    replay = []
+    for _ in range(2):
+        trk.init(frames[8], start_frame_i=8, time_direction=-1, flow_cache=dcache)
+        replay.append([trk.track(frames[t]).result.packed().clone() for t in range(7, -1, -1)])
+    assert dcache.writes == finite_pairs and dcache.hits == finite_pairs
+    for a, b, c in zip(runs[0], replay[0], replay[1]):
+        assert torch.equal(a.cpu(), b.cpu()) and torch.equal(b.cpu(), c.cpu())
 
 
 @pytest.mark.parametrize('size', [(512, 512), (1080, 1920)])

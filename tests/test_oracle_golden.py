@@ -134,3 +134,11 @@ def test_tracker_real_128(real_weights, which):
     ref = g[f'result_{which}']
     bad = (np.abs(got - ref) > 2e-3).any(0)
     assert bad.mean() < 0.01, bad.mean()
+
+
+def test_warp_forward_matches_reference():
+    """Forward splat: oracle restatement of FlowOUTrackingResult.warp_forward / bilinear_splat against the
+    vectors recorded from the unmodified reference (clamped corner indices, mask, border)."""
+    g = golden('warp_forward.npz')
+    assert np.abs(O.warp_forward(g['flow'], g['img']) - g['out_plain']).max() < 1e-6
+    assert np.abs(O.warp_forward(g['flow'], g['img'], g['mask'], -1.0) - g['out_mask']).max() < 1e-6
