@@ -130,6 +130,7 @@ struct ProgLayer {
 struct ConvProgram {
     ProgLayer L[kMaxProgLayers];
     int n_layers;
+    int tickets;                  // tiles a CTA may hold at once (scheduler run-ahead), 1..4; 0 = 4
     int iters;                    // the whole layer sequence is repeated `iters` times (iterations overlap tile by tile)
     LookupArgs lk;                // operands of the lookup layer, if any
     int nbatch, b0;               // batch entries covered by this launch

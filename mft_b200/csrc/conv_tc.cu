@@ -483,6 +483,7 @@ struct ProgCtl {
     uint32_t stored[kProgTickets];            // epilogue warps that have stored their part of the tile
     uint32_t tmem_base;
     uint32_t abort;
+    uint32_t depth;                           // tickets in flight per CTA (<= kProgTickets)
 };
 static_assert(sizeof(ProgCtl) <= 1024, "control block");
 
@@ -538,7 +539,7 @@ __device__ __forceinline__ void prog_decode(const ConvProgram& P, uint32_t item,
 
 // Waits for ticket slot n % kProgTickets and returns its ticket (kTicketEnd on time-out, which ends the role).
 __device__ __forceinline__ uint32_t prog_take_ticket(volatile ProgCtl* ctl, uint32_t n) {
-    const uint32_t slot = n % kProgTickets, par = (n / kProgTickets) & 1u;
+    const uint32_t slot = n % ctl->depth, par = (n / ctl->depth) & 1u;
     if (!__all_sync(0xffffffffu, mbar_wait(const_cast<uint64_t*>(&ctl->tk_full[slot]), par))) {
         ctl->abort = 50;
         return kTicketEnd;
@@ -547,7 +548,7 @@ __device__ __forceinline__ uint32_t prog_take_ticket(volatile ProgCtl* ctl, uint
 }
 __device__ __forceinline__ void prog_release_ticket(volatile ProgCtl* ctl, uint32_t n) {
     __syncwarp();
-    if (elect_one()) mbar_arrive(const_cast<uint64_t*>(&ctl->tk_empty[n % kProgTickets]));
+    if (elect_one()) mbar_arrive(const_cast<uint64_t*>(&ctl->tk_empty[n % ctl->depth]));
 }
 
 // LOOKUP: the program may contain a lookup layer (compiled apart: its code would only cost the plain program registers)
@@ -580,6 +581,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
         }
         fence_mbar_init();
         ctl->abort = 0;
+        ctl->depth = static_cast<uint32_t>(P.tickets);
     }
     if (threadIdx.x < 2 * P.n_layers) {
         const ProgLayer& L = P.L[threadIdx.x >> 1];
@@ -617,13 +619,14 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             for (int r = static_cast<int>(blockIdx.x) * 32 + lane; r < per_layer; r += static_cast<int>(gridDim.x) * 32)
                 push(static_cast<uint32_t>(l * per_layer + r));
         }
+        const uint32_t depth = static_cast<uint32_t>(P.tickets);
         uint32_t n_issue = 0, n_done = 0, my_item = 0, idx = 0, spins = 0;
         bool have_idx = false, end_posted = false;
         for (;;) {
             bool progress = false;
             // ---- completed tiles of this CTA, in ticket order: count in at every successor tile, push those that become ready
             while (n_done < n_issue) {
-                const uint32_t slot = n_done % kProgTickets;
+                const uint32_t slot = n_done % depth;
                 uint32_t st;
                 asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];"
                              : "=r"(st) : "r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[slot]))) : "memory");
@@ -659,10 +662,10 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             }
             if (end_posted) {
                 if (n_done == n_issue) break;
-            } else if (n_issue - n_done < static_cast<uint32_t>(kProgTickets)) {
-                const uint32_t slot = n_issue % kProgTickets;
+            } else if (n_issue - n_done < depth) {
+                const uint32_t slot = n_issue % depth;
                 uint32_t room = 0;
-                if (lane == 0) room = mbar_try_wait(const_cast<uint64_t*>(&ctl->tk_empty[slot]), ((n_issue / kProgTickets) & 1u) ^ 1u) ? 1u : 0u;
+                if (lane == 0) room = mbar_try_wait(const_cast<uint64_t*>(&ctl->tk_empty[slot]), ((n_issue / depth) & 1u) ^ 1u) ? 1u : 0u;
                 if (__shfl_sync(0xffffffffu, room, 0) != 0u) {
                     if (!have_idx) {
                         if (lane == 0) {
@@ -863,7 +866,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             __syncwarp();
             if (elect_one())
                 asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;"
-                             ::"r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[n % kProgTickets]))) : "memory");
+                             ::"r"(smem_u32(const_cast<uint32_t*>(&ctl->stored[n % ctl->depth]))) : "memory");
             prog_release_ticket(ctl, n);
         }
     }
@@ -1476,6 +1479,7 @@ const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, int iters, c
     prog->nbatch = nbatch;
     prog->b0 = b0;
     prog->iters = iters;
+    if (prog->tickets < 1 || prog->tickets > kProgTickets) prog->tickets = kProgTickets;
     prog->epoch += 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));

@@ -856,6 +856,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "persist") == 0 && value >= 0 && value <= 2) { c->persist = value; return MFTB200_OK; }
+    if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }

@@ -43,6 +43,18 @@ print(f'persist vs layered: bit-identical={bool(torch.equal(res[0], res[1]))} ma
       f'flow mean|diff|={d[:, :2].mean().item():.3e}')
 
 eng.set_option('persist', 1)
+for tk in (1, 2, 3, 4):
+    eng.set_option('prog_tickets', tk)
+    eng.refine(lefts, rights)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        o2 = eng.refine(lefts, rights)
+    b.record()
+    torch.cuda.synchronize()
+    eng.check_device()
+    print(f'prog_tickets={tk}: {a.elapsed_time(b) / reps:.3f} ms  identical={bool(torch.equal(o2, res[1]))}')
 import ctypes
 torch.cuda.synchronize()
 z = torch.zeros(8192, dtype=torch.int64, device='cuda')

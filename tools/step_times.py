@@ -1,4 +1,6 @@
-"""Warm per-launch device times of one steady-state frame (CUDA events around every engine step)."""
+"""Warm per-launch device times of one steady-state frame (CUDA events around every engine step, serialised on one
+stream: no overlap between branches, so the groups add up to more than the frame time of bench.py)."""
+import collections
 import os
 import sys
 
@@ -7,6 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
+from mft_b200 import weights as W  # noqa: E402
 from mft_b200.synth import synthetic_video  # noqa: E402
 
 size = int(os.environ.get('PROFILE_SIZE', '512'))
@@ -18,35 +21,32 @@ t = 1
 for _ in range(bench.STEADY + 2):
     trk.track(frames[t], device_result=True); t += 1
 eng = trk.engine
-acc = None
 reps = 3
+groups = collections.OrderedDict()
 for r in range(reps):
     eng.set_option('profile', 1)
     trk.track(frames[t], device_result=True); t += 1
     st = eng.profile_steps()
     eng.profile_fetch()
     eng.set_option('profile', 0)
-    acc = [a + b[0] for a, b in zip(acc, st)] if acc else [b[0] for b in st]
-kinds = [k for _, k, _ in st]
-ENC = ['patches'] + [f'fnet{i}' for i in range(100)]
-tot = sum(acc) / reps
-print(f'{len(acc)} steps, total {tot * 1e3:.1f} us (events add ~2-4 us per step)')
-names_iter = ['lookup', 'convc1', 'convc2', 'convf1', 'convf2', 'convm', 'zr1', 'q1', 'zr2', 'q2', 'fh1', 'fh2']
-n_enc = len(acc) - 3 - 12 * 12 - 6
-for i, v in enumerate(acc):
-    us = v / reps * 1e3
-    if i < n_enc:
-        tag = f'enc[{i}]'
-    elif i < n_enc + 3:
-        tag = ['pair_setup', 'corr_gemm', 'corr_pool'][i - n_enc]
-    elif i < n_enc + 3 + 144:
-        j = i - n_enc - 3
-        tag = f'it{j // 12}:{names_iter[j % 12]}'
-        if j // 12 not in (0, 5, 11):
-            continue
-    else:
-        tag = ['mask1', 'mask2', 'ou_pack', 'ou1', 'ou2', 'upsample'][i - n_enc - 147]
-    print(f'{i:4d} {us:8.1f} us  kind={kinds[i]}  {tag}')
-enc = sum(acc[:n_enc]) / reps * 1e3
-it = sum(acc[n_enc + 3:n_enc + 147]) / reps * 1e3
-print(f'encoders {enc:.0f} us, pre {sum(acc[n_enc:n_enc+3]) / reps * 1e3:.0f} us, 12 iterations {it:.0f} us, final {sum(acc[n_enc+147:]) / reps * 1e3:.0f} us')
+    seen_prog = False
+    for ms, kind, layer in st:
+        if layer == 200 or layer == 201:
+            name, seen_prog = 'iteration program (conv_prog_kernel)', True
+        elif layer == 100:
+            name = 'correlation GEMM'
+        elif 0 <= layer < 16:
+            name = 'fnet convs'
+        elif 16 <= layer < 32:
+            name = 'cnet convs'
+        elif 0 <= layer < len(W.LAYER_NAMES):
+            name = 'heads: ' + W.LAYER_NAMES[layer]
+        else:
+            name = 'other kernels after the loop (ou_pack, upsample)' if seen_prog else 'other kernels before / inside the loop (patches, instance norm, pair setup, pool, lookup)'
+        g = groups.setdefault(name, [0.0, 0])
+        g[0] += ms
+        g[1] += 1
+tot = sum(v[0] for v in groups.values()) / reps
+print(f'{sum(v[1] for v in groups.values()) // reps} steps, serialised total {tot * 1e3:.0f} us (events add ~2-4 us per step)')
+for k, (ms, n) in groups.items():
+    print(f'{ms / reps * 1e3:9.1f} us  {n // reps:4d} launches  {k}')
