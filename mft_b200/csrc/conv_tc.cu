@@ -1,11 +1,13 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.  See conv.h for the contract.
 //
-// CTA = 192 threads, one 128-pixel x n_tile output tile:
-//   warp 0   : TMA producer  (one elected lane; A box = shifted activation tile, B box = weight slab)
-//   warp 1   : TMEM allocator + tcgen05.mma issuer (one elected lane, 4 x K=16 MMAs per stage)
-//   warps 2-5: epilogue (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> HBM)
-// Pipeline: `stages` smem slots guarded by full/empty mbarriers; accumulator hand-off through a
-// third mbarrier signalled by tcgen05.commit.
+// Two kernels share the operand pipeline and the fused epilogues:
+//   conv_tc_kernel    one launch per layer; CTA = 256 threads = one 128-pixel x n_tile output tile, two CTAs per SM.
+//                     warp 0 = A-operand TMA producer (shifted activation box per tap), warp 2 = B-operand TMA producer
+//                     (weight slab), warp 1 = TMEM allocator + tcgen05.mma issuer (4 x K=16 MMAs per 64-channel stage);
+//                     `stages` smem slots guarded by full/empty mbarriers, accumulator hand-off through a third mbarrier
+//                     signalled by tcgen05.commit; then all 8 warps drain the accumulator (tile_epilogue).
+//   conv_prog_kernel  persistent: one CTA per SM runs a whole program of dependent layers (a GRU iteration) with
+//                     tile-level dataflow, warp-specialised roles and two TMEM accumulators (see below).
 #include <cstddef>
 #include <cstdio>
 #include <type_traits>
@@ -457,8 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Shared-memory map (one CTA per SM, 384 threads):
 //   [0, 192K)     operand ring: 4 slots x 48 KiB (A box 16 KiB + B slab <= 32 KiB), the same slots for every layer
 //   [192K, 224K)  epilogue staging, 8 warps x 4 KiB
-//   [224K, 225K)  bias of the tile being drained
-//   [225K, 226K)  control block: mbarriers, TMEM base, ticket ring
+//   [224K, 225K)  control block: mbarriers, TMEM base, ticket ring
 // Warp roles:  0 = A-operand producer   1 = MMA issuer   2 = B-operand producer   3 = scheduler (tickets + dependencies)
 //              4..11 = epilogue (warp w drains TMEM lane quarter w % 4, column chunks of parity (w - 4) / 4)
 // The last epilogue warp to finish a tile raises its completion flag.
@@ -469,8 +470,7 @@ constexpr int kProgThreads = 384;      // 12 warps = 3 per SM sub-partition: up 
 constexpr int kProgStages = 4;
 constexpr uint32_t kProgSlotBytes = 48 * 1024;
 constexpr uint32_t kProgStagingOff = kProgStages * kProgSlotBytes;
-constexpr uint32_t kProgBiasOff = kProgStagingOff + 8 * 4096;
-constexpr uint32_t kProgCtlOff = kProgBiasOff + 1024;
+constexpr uint32_t kProgCtlOff = kProgStagingOff + 8 * 4096;
 constexpr uint32_t kProgSmemBytes = kProgCtlOff + 1024;
 constexpr int kProgTickets = 4;
 constexpr uint32_t kTicketEnd = 0xffffffffu;
@@ -489,9 +489,6 @@ static_assert(sizeof(ProgCtl) <= 1024, "control block");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Correlation-pyramid lookup of one tile's 128 pixels by the 8 epilogue warps: 16 pixels per warp, two in flight (2 x 1664 B

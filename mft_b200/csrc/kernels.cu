@@ -252,34 +252,41 @@ void launch_warp_forward(const float* flow, const float* img, const uint8_t* mas
 // ==========================================================================================
 // frame -> im2col patches for the 7x7/2 first conv (MFT/raft.py:41-48, core/raft.py:122-124)
 // ==========================================================================================
+// one thread = 8 consecutive patch entries (one 16-byte store); 152 = 19 x 8 entries per output pixel
 __global__ void __launch_bounds__(256)
 frame_patches_kernel(const uint8_t* __restrict__ bgr, int H, int W, int Hp, int Wp, int pl, int pt,
-                     __half* __restrict__ patches, long total) {
+                     __half* __restrict__ patches, long total8) {
     pdl_enter();
     const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int k = static_cast<int>(i % 152);
-    const long op = i / 152;
+    if (i >= total8) return;
+    const int seg = static_cast<int>(i % 19);
+    const long op = i / 19;
     const int Wo = Wp / 2;
-    const int oy = static_cast<int>(op / Wo), ox = static_cast<int>(op % Wo);
-    float v = 0.0f;
-    if (k < 147) {
-        const int c = k % 3, kx = (k / 3) % 7, ky = k / 21;
-        const int yp = 2 * oy + ky - 3, xp = 2 * ox + kx - 3;
-        if (yp >= 0 && yp < Hp && xp >= 0 && xp < Wp) {
-            const int ys = min(max(yp - pt, 0), H - 1), xs = min(max(xp - pl, 0), W - 1);
-            const float u = static_cast<float>(bgr[(static_cast<long>(ys) * W + xs) * 3 + (2 - c)]);
-            v = 2.0f * (u / 255.0f) - 1.0f;
+    const int oy = static_cast<int>(op / Wo), ox = static_cast<int>(op - static_cast<long>(oy) * Wo);
+    __align__(16) __half v8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = seg * 8 + j;
+        float v = 0.0f;
+        if (k < 147) {
+            const int tap = k / 3, c = k - tap * 3, ky = tap / 7, kx = tap - ky * 7;
+            const int yp = 2 * oy + ky - 3, xp = 2 * ox + kx - 3;
+            if (yp >= 0 && yp < Hp && xp >= 0 && xp < Wp) {
+                const int ys = min(max(yp - pt, 0), H - 1), xs = min(max(xp - pl, 0), W - 1);
+                const float u = static_cast<float>(__ldg(bgr + (static_cast<long>(ys) * W + xs) * 3 + (2 - c)));
+                v = 2.0f * (u / 255.0f) - 1.0f;
+            }
         }
+        v8[j] = __float2half_rn(v);
     }
-    patches[i] = __float2half_rn(v);
+    *reinterpret_cast<uint4*>(patches + i * 8) = *reinterpret_cast<const uint4*>(v8);
 }
 
 void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
                           cudaStream_t stream) {
-    const long total = static_cast<long>(Hp / 2) * (Wp / 2) * 152;
-    launch_pdl(frame_patches_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, bgr, H, W, Hp,
-               Wp, pad_left, pad_top, patches, total);
+    const long total8 = static_cast<long>(Hp / 2) * (Wp / 2) * 19;
+    launch_pdl(frame_patches_kernel, dim3(static_cast<unsigned>((total8 + 255) / 256)), dim3(256), 0, stream, bgr, H, W, Hp,
+               Wp, pad_left, pad_top, patches, total8);
 }
 
 // ==========================================================================================
@@ -480,7 +487,7 @@ lookup_kernel(const LookupArgs a) {
     if (p0 >= total) return;
     const LookupLane t = lookup_lane_init(lane);
     const int npx = a.h * a.w;
-    const int n0 = static_cast<int>(p0 % npx);
+    const int n0 = static_cast<int>(static_cast<unsigned>(p0) % static_cast<unsigned>(npx));      // total < 2^31 pixels (32-bit remainder)
     LookupPixel px[kLkPixPerWarp];
 #pragma unroll
     for (int i = 0; i < kLkPixPerWarp; ++i)

@@ -72,18 +72,24 @@ __device__ __forceinline__ void lookup_gather(const LookupArgs& a, const LookupL
     px.cx = c.x;
     px.cy = c.y;
     px.finite = isfinite(c.x) && isfinite(c.y);
+    // lane l & 3 evaluates level l & 3 (position round trip, fractions, window origin); the level loop then only
+    // broadcasts the four numbers instead of every lane redoing all four levels
+    const int myl = lane & 3;
+    const int mh = a.h >> myl, mw = a.w >> myl;
+    const float inv = 1.0f / static_cast<float>(1 << myl);          // 1 / 2^level: exact
+    const float fxp = lk_roundtrip_div(c.x * inv - 4.0f, static_cast<float>(mw - 1));
+    const float fyp = lk_roundtrip_div(c.y * inv - 4.0f, static_cast<float>(mh - 1));
+    const float fx = floorf(fxp), fy = floorf(fyp);
+    const float my_wE = fxp - fx, my_wS = fyp - fy;
+    // non-finite coordinates: park the window outside the map, every tap then reads as zero (the output is NaN anyway)
+    const int my_X0 = px.finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(mw + 16))) : -64;
+    const int my_Y0 = px.finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(mh + 16))) : -64;
     int hl = a.h, wl = a.w;
-    float inv = 1.0f;                                   // 1 / 2^level: the division by 2^level is exact either way
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        const float fxp = lk_roundtrip_div(c.x * inv - 4.0f, static_cast<float>(wl - 1));
-        const float fyp = lk_roundtrip_div(c.y * inv - 4.0f, static_cast<float>(hl - 1));
-        const float fx = floorf(fxp), fy = floorf(fyp);
-        px.wE[l] = fxp - fx;
-        px.wS[l] = fyp - fy;
-        // non-finite coordinates: park the window outside the map, every tap then reads as zero (the output is NaN anyway)
-        const int X0 = px.finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(wl + 16))) : -64;
-        const int Y0 = px.finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(hl + 16))) : -64;
+        px.wE[l] = __shfl_sync(0xffffffffu, my_wE, l);
+        px.wS[l] = __shfl_sync(0xffffffffu, my_wS, l);
+        const int X0 = __shfl_sync(0xffffffffu, my_X0, l), Y0 = __shfl_sync(0xffffffffu, my_Y0, l);
         const float* base = a.lvl[l] + pp * static_cast<long>(hl * wl);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -94,7 +100,7 @@ __device__ __forceinline__ void lookup_gather(const LookupArgs& a, const LookupL
                 win[l * kLkLevelFloats + lane + 32 * k] = v;
             }
         }
-        hl >>= 1; wl >>= 1; inv *= 0.5f;
+        hl >>= 1; wl >>= 1;
     }
 }
 
