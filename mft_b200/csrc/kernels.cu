@@ -342,8 +342,10 @@ instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict_
     const int c2 = C / 2;
     const long per_img2 = static_cast<long>(P) * c2;
     const long i0 = static_cast<long>(blockIdx.x) * (blockDim.x * 8);
-    const int b = static_cast<int>(i0 / per_img2);          // a block never straddles two images (P*C/2 % 2048 == 0 is not
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {     //  required: stragglers recompute below)
+    // element counts < 2^31: 32-bit divisions.  A block never straddles two images (P*C/2 % 2048 == 0 is not required:
+    // stragglers recompute below)
+    const int b = static_cast<int>(static_cast<unsigned>(i0) / static_cast<unsigned>(per_img2));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double* s = sums + static_cast<long>(b) * 2 * C;
         const double inv = 1.0 / P;
         const double m = s[c] * inv;
@@ -356,9 +358,9 @@ instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict_
     for (int k = 0; k < 8; ++k) {
         const long i = i0 + static_cast<long>(k) * blockDim.x + threadIdx.x;
         if (i >= total2) break;
-        const int cp = static_cast<int>(i % c2);
+        const int cp = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(c2));
         float m0 = s_mean[2 * cp], m1 = s_mean[2 * cp + 1], r0 = s_rstd[2 * cp], r1 = s_rstd[2 * cp + 1];
-        if (i / per_img2 != b) {                              // rare: element of the next image inside this block
+        if (static_cast<int>(static_cast<unsigned>(i) / static_cast<unsigned>(per_img2)) != b) {                              // rare: element of the next image inside this block
             const double* s = sums + (i / per_img2) * 2 * C;
             const double inv = 1.0 / P;
             const double a0 = s[2 * cp] * inv, a1 = s[2 * cp + 1] * inv;
@@ -398,7 +400,7 @@ pair_setup_kernel(const PairSetup a) {
     const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);      // pair * npx + n
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
     const int lane = threadIdx.x & 31;
-    const int pair = static_cast<int>(pp / npx), n = static_cast<int>(pp % npx);
+    const int pair = static_cast<int>(static_cast<unsigned>(pp) / static_cast<unsigned>(npx)), n = static_cast<int>(pp) - pair * npx;
     const int ls = a.slots[2 * pair], rs = a.slots[2 * pair + 1];
     const long lsrc = static_cast<long>(ls) * npx + n, rsrc = static_cast<long>(rs) * npx + n;
     // fmaps: 256 halves = 32 x uint4 per pixel
@@ -521,7 +523,7 @@ ou_pack_kernel(const OuPackArgs a) {
     const long pp = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
     const int lane = threadIdx.x & 31;
-    const int n = static_cast<int>(pp % npx);
+    const int n = static_cast<int>(static_cast<unsigned>(pp) % static_cast<unsigned>(npx));
     const uint4* X = reinterpret_cast<const uint4*>(a.X + pp * 512);          // 64 chunks
     const uint4* C = reinterpret_cast<const uint4*>(a.corr16 + pp * 328);     // 41 chunks (row pitch 656 B)
     uint4* o = reinterpret_cast<uint4*>(a.packed + pp * 720);                  // 90 chunks
@@ -565,7 +567,7 @@ upsample_kernel(const UpsampleArgs a) {
     if (pp >= static_cast<long>(a.n_pairs) * npx) return;
     const int sub = threadIdx.x & 63;
     const int sy = sub >> 3, sx = sub & 7;
-    const int pair = static_cast<int>(pp / npx), n = static_cast<int>(pp % npx);
+    const int pair = static_cast<int>(static_cast<unsigned>(pp) / static_cast<unsigned>(npx)), n = static_cast<int>(pp) - pair * npx;
     const int y = n / a.w, x = n % a.w;
     const float* m = a.mask32 + pp * 576 + sub;
     float mk[9];
