@@ -633,6 +633,11 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                 prog_decode(P, item, it, l, b, tile);
                 const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
                 const ProgLayer& L = P.L[l];
+                if (P.timing != nullptr && lane == 0) {                     // tuning aid: when did this layer's last tile finish
+                    unsigned long long gt;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    atomicMax(reinterpret_cast<unsigned long long*>(P.timing) + 4096 + 2 * l + 1, gt);
+                }
 #pragma unroll
                 for (int si = 0; si < 2; ++si) {            // one pass per successor layer, one lane per tile of its 5x5 reach
                     const int sl = si == 0 ? L.succ0 : L.succ1;
@@ -686,6 +691,13 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                         entry = __shfl_sync(0xffffffffu, entry, 0);
                         if ((entry >> 32) == P.epoch) {
                             const uint32_t item = static_cast<uint32_t>(entry);
+                            if (P.timing != nullptr && lane == 0) {         // tuning aid: when was this layer's first tile handed out
+                                unsigned long long gt;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                                int it2, l2, b2, t2;
+                                prog_decode(P, item, it2, l2, b2, t2);
+                                atomicMin(reinterpret_cast<unsigned long long*>(P.timing) + 4096 + 2 * l2, gt);
+                            }
                             fence_proxy_async_all();
                             if (lane == static_cast<int>(slot)) my_item = item;
                             if (lane == 0) {

@@ -99,6 +99,7 @@ struct mftb200_ctx {
     // program (correct, but the lookup is latency-bound on 8 warps per SM: slower, kept as an option under test)
     int persist = 1;
     ConvProgram prog, prog_full;
+    long long* prog_timing = nullptr;      // role timers of the program kernel, written only with option "prog_timing"
     bool prog_ok = false, prog_full_ok = false;
     int lookup_step = -1;
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
@@ -418,9 +419,10 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             P.queue_cap = static_cast<int>(iters_cap * kMaxProgLayers * mp * tiles);
             P.queue = c->dalloc<unsigned long long>(P.queue_cap);
             P.arrivals = c->dalloc<int>(2 * static_cast<size_t>(kMaxProgLayers) * mp * tiles);
-            P.timing = c->dalloc<long long>(8 * 1024);
-            return hq != nullptr && P.queue != nullptr && P.arrivals != nullptr && P.timing != nullptr;
+            P.timing = nullptr;
+            return hq != nullptr && P.queue != nullptr && P.arrivals != nullptr;
         };
+        c->prog_timing = c->dalloc<long long>(8 * 1024);
         memset(&c->prog, 0, sizeof c->prog);
         const char* pe = nullptr;
         for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], depsA[k][0], depsA[k][1], true);
@@ -856,6 +858,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "persist") == 0 && value >= 0 && value <= 2) { c->persist = value; return MFTB200_OK; }
+    if (strcmp(key, "prog_timing") == 0) { c->prog.timing = c->prog_full.timing = value ? c->prog_timing : nullptr; return MFTB200_OK; }
     if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
@@ -920,7 +923,7 @@ int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* b
         {"corr_l3", c->corr[3], c->corr_bytes[3]}, {"corr16", c->corr16, M * 328 * 2}, {"X", c->X, M * 512 * 2},
         {"h32", c->h32, M * 128 * 4}, {"coords1", c->coords1, M * 2 * 4}, {"delta32", c->delta32, M * 2 * 4},
         {"mask32", c->mask32, M * 576 * 4}, {"ou32", c->ou32, M * 4 * 4}, {"patches", c->patches, 0},
-        {"prog_timing", c->prog.timing, 8 * 1024 * 8}, {"E0", c->E[0], 0}, {"E1", c->E[1], 0}, {"flowpatch", c->flowpatch, M * 104 * 2}, {"cf", c->cf, M * 256 * 2},
+        {"prog_timing", c->prog_timing, 8 * 1024 * 8}, {"E0", c->E[0], 0}, {"E1", c->E[1], 0}, {"flowpatch", c->flowpatch, M * 104 * 2}, {"cf", c->cf, M * 256 * 2},
     };
     for (const Ent& e : tab)
         if (strcmp(e.n, name) == 0) { *ptr = e.p; *bytes = e.b; return MFTB200_OK; }
