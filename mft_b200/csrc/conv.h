@@ -116,12 +116,13 @@ struct ProgLayer {
     ConvEpi e;
     int mode;
     int dep0, dep1;               // program layers whose 3x3 tile neighbourhood (same batch entry) must be complete, -1 = none
-    int succ0, succ1;             // layers that list this one as a dependency (filled by conv_prog_add), -1 = none
+    int succ[4];                  // layers that list this one as a dependency (filled by conv_prog_finish), -1 = none
     int n_dep;                    // number of valid dependencies (0 = root layer: its tiles are ready at launch)
     int kind;                     // 0 = convolution, 1 = correlation-pyramid lookup tile (no MMA; run by the epilogue warps)
     int iter_shift;               // 1: the dependencies are the PREVIOUS iteration's tiles (iteration 0 is ready at launch)
     int ry, rx;                   // dependency radius in tiles: the predecessor tiles within +-ry / +-rx must be complete
-    int pad_[2];
+    int ny;                       // which n_tile-wide slice of the layer's output channels this program layer computes
+    int pad_[3];
 };
 
 // Work distribution is a dataflow ready queue in global memory: a tile is pushed when the last of its predecessor
@@ -150,7 +151,7 @@ struct ConvProgram {
 // Appends plan `p` as the next layer of `prog` (checks the common geometry).  Returns nullptr or an error string.
 // exact_halo: wait only for the predecessor tiles this layer's window actually reads (kh > 1: above / below, kw > 1:
 // left / right); otherwise for the whole 3x3 neighbourhood (needed when iterations overlap inside one launch).
-const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1, bool exact_halo);
+const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1, bool exact_halo, int ny = 0);
 // Appends a lookup layer (tile geometry of `like`) that depends on layer `dep` of the PREVIOUS iteration (a later
 // layer of the sequence, wired up by conv_prog_finish).
 const char* conv_prog_add_lookup(ConvProgram* prog, const ConvPlan& like, const LookupArgs& lk, int dep_prev_iter);

@@ -639,8 +639,8 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                     atomicMax(reinterpret_cast<unsigned long long*>(P.timing) + 4096 + 2 * l + 1, gt);
                 }
 #pragma unroll
-                for (int si = 0; si < 2; ++si) {            // one pass per successor layer, one lane per tile of its 5x5 reach
-                    const int sl = si == 0 ? L.succ0 : L.succ1;
+                for (int si = 0; si < 4; ++si) {            // one pass per successor layer, one lane per tile of its 5x5 reach
+                    const int sl = L.succ[si];
                     if (sl < 0 || lane >= 25) continue;
                     const ProgLayer& S = P.L[sl];
                     const int dy = lane / 5 - 2, dx = lane - (lane / 5) * 5 - 2;
@@ -765,7 +765,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             const ProgLayer& L = P.L[l];
             const ConvGeom& g = L.g;
             const int T = L.kind == 0 ? g.ntaps * g.kchunks : 0;
-            const int brow = b * g.b_rows_per_batch;
+            const int brow = b * g.b_rows_per_batch + L.ny * g.n_tile;
             const uint32_t b_bytes = static_cast<uint32_t>(g.n_tile) * 128;
             bool ok = true;
             for (int it = 0; it < T; ++it, ++it_glob) {
@@ -856,11 +856,11 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                 }
             } else if (ok_acc) {
                 switch (L.mode) {
-                    case EPI_F16: tile_epilogue<EPI_F16, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
-                    case EPI_F32: tile_epilogue<EPI_F32, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
-                    case EPI_GRU_ZR: tile_epilogue<EPI_GRU_ZR, 1024, LOOKUP ? 1 : 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
-                    case EPI_GRU_Q: tile_epilogue<EPI_GRU_Q, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
-                    case EPI_FLOW: tile_epilogue<EPI_FLOW, 1024, 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, 0, nullptr); break;
+                    case EPI_F16: tile_epilogue<EPI_F16, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, L.ny, nullptr); break;
+                    case EPI_F32: tile_epilogue<EPI_F32, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, L.ny, nullptr); break;
+                    case EPI_GRU_ZR: tile_epilogue<EPI_GRU_ZR, 1024, LOOKUP ? 1 : 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, L.ny, nullptr); break;
+                    case EPI_GRU_Q: tile_epilogue<EPI_GRU_Q, 1024, 1, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, L.ny, nullptr); break;
+                    case EPI_FLOW: tile_epilogue<EPI_FLOW, 1024, 2, true>(g, e, stg, nullptr, nullptr, acc, ew, lane, tx, ty, b, L.ny, nullptr); break;
                     default: break;
                 }
             }
@@ -1386,10 +1386,10 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
 // ------------------------------------------------------------------------------------------
 // layer programs (host side)
 // ------------------------------------------------------------------------------------------
-const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1, bool exact_halo) {
+const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int dep1, bool exact_halo, int ny) {
     if (prog->n_layers >= kMaxProgLayers) return "conv_prog_add: too many layers";
     const ConvGeom& g = p.g;
-    if (p.variant != 1 || g.cluster != 1 || g.n_tiles != 1) return "conv_prog_add: layer needs the plain 128-pixel kernel, one cout tile";
+    if (p.variant != 1 || g.cluster != 1 || ny < 0 || ny >= g.n_tiles) return "conv_prog_add: layer needs the plain 128-pixel kernel / bad cout slice";
     if (p.mode == EPI_CNET || p.e.stats != nullptr || p.e.res16 != nullptr) return "conv_prog_add: unsupported epilogue";
     if (kTileM * 128 + g.n_tile * 128 > static_cast<int>(kProgSlotBytes)) return "conv_prog_add: stage does not fit a ring slot";
     if (prog->n_layers == 0) {
@@ -1401,7 +1401,9 @@ const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int de
     if (dep0 >= prog->n_layers || dep1 >= prog->n_layers) return "conv_prog_add: dependency on a later layer";
     ProgLayer& L = prog->L[prog->n_layers++];
     L.tmA = p.tmA; L.tmB = p.tmB; L.g = p.g; L.e = p.e; L.mode = p.mode; L.dep0 = dep0; L.dep1 = dep1;
-    L.succ0 = L.succ1 = -1;
+    for (int& x : L.succ) x = -1;
+    L.ny = ny;
+    L.pad_[0] = L.pad_[1] = L.pad_[2] = 0;
     L.n_dep = (dep0 >= 0) + (dep1 >= 0);
     L.kind = 0;
     L.iter_shift = 0;
@@ -1411,7 +1413,6 @@ const char* conv_prog_add(ConvProgram* prog, const ConvPlan& p, int dep0, int de
     L.rx = (g.kw / 2 + g.tile_w - 1) / g.tile_w;
     if (!exact_halo) { L.ry = L.ry > 1 ? L.ry : 1; L.rx = L.rx > 1 ? L.rx : 1; }
     if (L.ry > 2 || L.rx > 2) { --prog->n_layers; return "conv_prog_add: tile too small for this layer's halo"; }
-    L.pad_[0] = L.pad_[1] = 0;
     L.g.b0 = 0;
     return nullptr;
 }
@@ -1431,7 +1432,7 @@ const char* conv_prog_add_lookup(ConvProgram* prog, const ConvPlan& like, const 
     L.g.b0 = 0;
     L.mode = EPI_F16;
     L.dep0 = dep_prev_iter; L.dep1 = -1;
-    L.succ0 = L.succ1 = -1;
+    for (int& x : L.succ) x = -1;
     L.n_dep = 1;
     L.kind = 1;
     L.iter_shift = 1;
@@ -1443,7 +1444,8 @@ const char* conv_prog_add_lookup(ConvProgram* prog, const ConvPlan& like, const 
 }
 
 const char* conv_prog_finish(ConvProgram* prog) {
-    for (int i = 0; i < prog->n_layers; ++i) prog->L[i].succ0 = prog->L[i].succ1 = -1;
+    for (int i = 0; i < prog->n_layers; ++i)
+        for (int& x : prog->L[i].succ) x = -1;
     for (int i = 0; i < prog->n_layers; ++i) {
         const ProgLayer& L = prog->L[i];
         for (int d : {L.dep0, L.dep1}) {
@@ -1451,9 +1453,10 @@ const char* conv_prog_finish(ConvProgram* prog) {
             if (d >= prog->n_layers) return "conv_prog_finish: dependency on a missing layer";
             if (L.iter_shift == 0 && d >= i) return "conv_prog_finish: same-iteration dependency on a later layer";
             ProgLayer& D = prog->L[d];
-            if (D.succ0 < 0) D.succ0 = i;
-            else if (D.succ1 < 0) D.succ1 = i;
-            else return "conv_prog_finish: a layer can feed at most two others";
+            int k = 0;
+            while (k < 4 && D.succ[k] >= 0) ++k;
+            if (k == 4) return "conv_prog_finish: a layer can feed at most four others";
+            D.succ[k] = i;
         }
     }
     return nullptr;

@@ -98,7 +98,9 @@ struct mftb200_ctx {
     // 1 = one launch per iteration (default), 2 = ONE launch for all iterations with the pyramid lookup as tiles of the
     // program (correct, but the lookup is latency-bound on 8 warps per SM: slower, kept as an option under test)
     int persist = 1;
-    ConvProgram prog, prog_full;
+    ConvProgram prog, prog_full, prog_heads;   // prog_heads: mask head || OU head after the last iteration
+    bool prog_heads_ok = false;
+    int fz_ou_pack = -1, fz_upsample = -1;
     long long* prog_timing = nullptr;      // role timers of the program kernel, written only with option "prog_timing"
     bool prog_ok = false, prog_full_ok = false;
     int lookup_step = -1;
@@ -439,7 +441,9 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     auto& Fz = c->final_steps;
     Act a_ou1{c->c1buf, 256, 256, h, w};       // the OU branch keeps its hidden layer in c1buf (free after the last iteration)
     Fz.push_back(sync_step(1));
-    Fz.push_back(B.step(B.conv16(L_MASK1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    int ph[4];       // plan indices: mask1, mask2, ou1, ou2
+    Fz.push_back(B.step(ph[0] = B.conv16(L_MASK1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    c->fz_ou_pack = static_cast<int>(Fz.size());
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
         OuPackArgs a{cc->X + o * 512, cc->corr16 + o * 328, cc->coords1 + o * 2, cc->delta32 + o * 2, cc->oupack + o * 720,
@@ -456,9 +460,10 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             e.scale = 0.25f; e.out32 = c->mask32; e.out32_stride = 576; e.n_valid = 576;   // update.py:237
         }
         Fz.push_back(B.step(i, true));
+        ph[1] = i;
     }
     Act a_ou{c->oupack, 720, 712, h, w};
-    Fz.push_back(B.step(B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->c1buf, 256, 0, 256), true));
+    Fz.push_back(B.step(ph[2] = B.conv16(L_OU1, a_ou, mp, 1, t3, 256, 1, c->c1buf, 256, 0, 256), true));
     Fz.back().lane = 1;
     {
         const int i = B.conv(L_OU2, a_ou1, mp, 1, t3, 16, EPI_F32);
@@ -468,6 +473,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         }
         Fz.push_back(B.step(i, true));
         Fz.back().lane = 1;
+        ph[3] = i;
     }
     Fz.push_back(sync_step(2));
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
@@ -479,6 +485,29 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         cc->launches++;
         return nullptr;
     });
+    c->fz_upsample = static_cast<int>(Fz.size()) - 1;
+    // the four head convolutions as ONE persistent launch: mask1 -> mask2 (three 192-channel slices) || ou1 -> ou2
+    c->prog_heads_ok = false;
+    if (!B.err) {
+        memset(&c->prog_heads, 0, sizeof c->prog_heads);
+        ConvProgram& P = c->prog_heads;
+        const char* pe = conv_prog_add(&P, c->plans[ph[0]], -1, -1, true);
+        for (int ny = 0; ny < 3 && !pe; ++ny) pe = conv_prog_add(&P, c->plans[ph[1]], 0, -1, true, ny);
+        if (!pe) pe = conv_prog_add(&P, c->plans[ph[2]], -1, -1, true);
+        if (!pe) pe = conv_prog_add(&P, c->plans[ph[3]], 4, -1, true);
+        if (!pe && !conv_prog_finish(&P)) {
+            P.max_batch = mp;
+            P.err_flag = c->err_flag;
+            const size_t tiles = static_cast<size_t>(P.tiles_x) * P.tiles_y;
+            unsigned long long* hq = c->dalloc<unsigned long long>(64);
+            P.head = hq;
+            P.tail = hq ? hq + 16 : nullptr;
+            P.queue_cap = static_cast<int>(kMaxProgLayers * mp * tiles);
+            P.queue = c->dalloc<unsigned long long>(P.queue_cap);
+            P.arrivals = c->dalloc<int>(2 * static_cast<size_t>(kMaxProgLayers) * mp * tiles);
+            c->prog_heads_ok = hq != nullptr && P.queue != nullptr && P.arrivals != nullptr;
+        }
+    }
     return B.err;
 }
 
@@ -789,7 +818,25 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
     } else {
         for (int it = 0; it < c->iters && r == MFTB200_OK; ++it) r = run_steps_groups(c, c->iter_steps, groups, n_groups);
     }
-    if (r == MFTB200_OK) r = run_steps_groups(c, c->final_steps, groups, n_groups);
+    if (r == MFTB200_OK && !layered && c->prog_heads_ok) {
+        c->cur_group = 0; c->cur_b0 = 0; c->cur_pairs = n_pairs;
+        {
+            mftb200_ctx::Step st = c->final_steps[c->fz_ou_pack];      // (a side-stream step of the per-layer path)
+            st.lane = 0;
+            r = run_one(c, st);
+        }
+        if (r == MFTB200_OK) {
+            mftb200_ctx::Step prog_step([](mftb200_ctx* cc, cudaStream_t st) -> const char* {
+                cc->launches++;
+                return conv_prog_launch(&cc->prog_heads, cc->cur_pairs, 0, 1, st);
+            }, 0);
+            prog_step.tag = 202;
+            r = run_one(c, prog_step);
+        }
+        if (r == MFTB200_OK) r = run_one(c, c->final_steps[c->fz_upsample]);
+    } else if (r == MFTB200_OK) {
+        r = run_steps_groups(c, c->final_steps, groups, n_groups);
+    }
     if (n_groups == 2) {
         cudaEventRecord(c->ev_done, c->gs[1][0]);
         cudaStreamWaitEvent(s, c->ev_done, 0);
