@@ -62,6 +62,7 @@ struct ConvEpi {
     float* delta32;               // [pixel][2]
     double* stats;                // optional [2][n_valid] per-channel sum / sum of squares of the (pre-activation) outputs,
                                   // accumulated with atomics: instance-norm statistics fused into the producing conv
+    int tma_store;                // EPI_F32 only: the output goes out as 32 x 32 bulk tensor stores (ConvPlan::tmO)
     int* err_flag;
     long long* timing;            // optional per-CTA phase timestamps [cta][8] (tuning aid), nullptr in product runs
 };
@@ -69,6 +70,7 @@ struct ConvEpi {
 // Fully described launch (built once per layer at configure time).
 struct ConvPlan {
     CUtensorMap tmA, tmB;
+    CUtensorMap tmO;              // output matrix [rows][out32_stride] fp32 for the bulk-store epilogue (conv_plan_enable_tma_store)
     ConvGeom g;
     int variant;                  // 1 = 128-pixel tile, one A box per tap; 2 = 256-pixel tile with haloed A (see conv_tc.cu)
     CUtensorMap tmA2;
@@ -94,6 +96,11 @@ void choose_tile(int H, int W, int* tile_h, int* tile_w);
 const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a_cin, int in_H, int in_W, int batch,
                            int stride, const TapList& taps, const __half* wt, int cout_pad, int n_tile,
                            int b_rows_per_batch, int force_tile_h, int force_tile_w);
+
+// For an EPI_F32 plan whose epilogue fields are set: store the output with bulk tensor stores (one 32 x 32 fp32 block per
+// instruction, clipped by TMA) instead of per-thread st.global.  Needs one-row tiles (GEMM view) and a dense row-major
+// output.  Returns nullptr when enabled or the reason why not.
+const char* conv_plan_enable_tma_store(ConvPlan* p, long rows);
 
 // Test / tuning override for the cluster size chosen by conv_plan_init (0 = automatic).
 void conv_set_forced_cluster(int c);

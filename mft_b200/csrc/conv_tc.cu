@@ -152,7 +152,7 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
 template <int MODE, int STG = 2048, int PRE = 0, bool LEAN = false>      // PRE: 0 = off, 1 = bias from global only, 2 = bias + input prefetch
 __device__ __forceinline__ void tile_epilogue(const ConvGeom& g, const ConvEpi& e, uint8_t* smem, const float* bw,
                                               float* stat_s, uint32_t tmem_base, int warp, int lane, int tx, int ty,
-                                              int b, int ny, long long* tstamp) {
+                                              int b, int ny, long long* tstamp, const CUtensorMap* tmO = nullptr) {
     const int q = warp & 3;
     const int cpar = warp >> 2;
     float* stg = reinterpret_cast<float*>(smem) + warp * STG;
@@ -188,6 +188,35 @@ __device__ __forceinline__ void tile_epilogue(const ConvGeom& g, const ConvEpi& 
         if (tt) tstamp[9 + (c >> 1) * 4] = clock64();
         if constexpr (STG < 2048) __syncwarp();      // single staging buffer: everyone is done reading the previous chunk
         float* buf = stg + (STG >= 2048 ? ((c >> 1) & 1) * 1024 : 0);
+        if constexpr (MODE == EPI_F32 && STG >= 2048) {
+            if (tmO != nullptr) {
+                // Bulk-store path (one-row tiles: the warp's 32 accumulator rows are 32 consecutive rows of the output
+                // matrix).  thread = row: scale / bias / relu in registers, the 32 x 32 block staged in TMA's 128-byte
+                // swizzle (the same XOR pattern as the transposing path), one cp.async.bulk.tensor store per block.
+                const int col0 = ny * g.n_tile + c * 32;
+                if (lane == 0) tma_store_wait_read<1>();          // the store that read this buffer two blocks ago is done
+                __syncwarp();
+                const float lo = e.relu ? 0.0f : -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * j));
+                    float4 v;
+                    v.x = fmaxf((__uint_as_float(r[4 * j]) + bb.x) * e.scale, lo);
+                    v.y = fmaxf((__uint_as_float(r[4 * j + 1]) + bb.y) * e.scale, lo);
+                    v.z = fmaxf((__uint_as_float(r[4 * j + 2]) + bb.z) * e.scale, lo);
+                    v.w = fmaxf((__uint_as_float(r[4 * j + 3]) + bb.w) * e.scale, lo);
+                    *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(tmO, buf, col0, tx * g.tile_w + q * 32, b);      // rows past the batch entry's end are clipped
+                    tma_store_commit();
+                }
+                continue;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
@@ -256,6 +285,12 @@ __device__ __forceinline__ void tile_epilogue(const ConvGeom& g, const ConvEpi& 
         }
         if (tt) tstamp[11 + (c >> 1) * 4] = clock64();
     }
+    if constexpr (MODE == EPI_F32 && STG >= 2048) {
+        if (tmO != nullptr) {
+            if (lane == 0) tma_store_wait_read<0>();              // the staging area may be reused / the CTA may exit
+            __syncwarp();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -265,8 +300,8 @@ constexpr int kThreads = 256;   // warp 0: TMA producer, warp 1: MMA issuer; aft
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
-               const ConvEpi e) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const ConvGeom g, const ConvEpi e) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = kTileM * 128;
@@ -420,7 +455,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ok = ok && ok_acc;
         if (tstamp && warp == 2 && lane == 0) tstamp[4] = clock64();
         tc_fence_after();
-        if (ok_acc) tile_epilogue<MODE>(g, e, smem, bw, stat_s, tmem_base, warp, lane, tx, ty, b, ny, tstamp);
+        if (ok_acc) tile_epilogue<MODE>(g, e, smem, bw, stat_s, tmem_base, warp, lane, tx, ty, b, ny, tstamp, e.tma_store ? &tmO : nullptr);
     }
     if (tstamp && warp == 2 && lane == 0) tstamp[5] = clock64();
     if (!ok && e.err_flag != nullptr) atomicExch(e.err_flag, 1 + warp);
@@ -1376,11 +1411,33 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, p.tmA, p.tmB, g, p.e);
+        cudaError_t lerr = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, p.tmA, p.tmB, p.tmO, g, p.e);
         if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     }
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
+const char* conv_plan_enable_tma_store(ConvPlan* p, long rows) {
+    p->e.tma_store = 0;
+    if (p->mode != EPI_F32 || p->variant != 1) return "tma store: EPI_F32 plans of the 128-pixel kernel only";
+    if (p->g.tile_h != 1 || p->g.H != 1) return "tma store: needs one-row tiles (GEMM view)";
+    if (p->e.out32 == nullptr || p->e.out32_coff != 0 || p->e.out32_stride % 4 != 0 || p->e.n_valid != p->e.out32_stride ||
+        (reinterpret_cast<uintptr_t>(p->e.out32) & 15) != 0)
+        return "tma store: output must be a dense, 16-byte aligned row-major matrix";
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return "cuTensorMapEncodeTiled entry point not available";
+    // (columns, rows of one batch entry, batch entries): a block never spills into the next batch entry's rows
+    const long batches = rows / p->g.W;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(p->e.out32_stride), static_cast<cuuint64_t>(p->g.W), static_cast<cuuint64_t>(batches)};
+    cuuint64_t str[2] = {static_cast<cuuint64_t>(p->e.out32_stride) * 4, static_cast<cuuint64_t>(p->e.out32_stride) * 4 * p->g.W};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(&p->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->e.out32, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "tma store: cuTensorMapEncodeTiled failed";
+    p->e.tma_store = 1;
+    return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------

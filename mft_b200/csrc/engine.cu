@@ -2,6 +2,7 @@
 // programs of the two encoders and of the batched refinement loop.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -98,6 +99,7 @@ struct mftb200_ctx {
     // 1 = one launch per iteration (default), 2 = ONE launch for all iterations with the pyramid lookup as tiles of the
     // program (correct, but the lookup is latency-bound on 8 warps per SM: slower, kept as an option under test)
     int persist = 1;
+    int tma_store = 1;                     // correlation volume written with bulk tensor stores (next configure)
     ConvProgram prog, prog_full, prog_heads;   // prog_heads: mask head || OU head after the last iteration
     bool prog_heads_ok = false;
     int fz_ou_pack = -1, fz_upsample = -1;
@@ -318,6 +320,11 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
             e.scale = 0.0625f; e.out32 = c->corr[0]; e.out32_stride = npx; e.out32_coff = 0; e.n_valid = npx;
+            c->plans[i].mode = EPI_F32;
+            if (c->tma_store) {                                    // else: per-thread stores
+                const char* why = conv_plan_enable_tma_store(&c->plans[i], static_cast<long>(mp) * npx);
+                if (getenv("MFTB200_DEBUG")) fprintf(stderr, "mft_b200: correlation bulk-store epilogue %s%s\n", why ? "off: " : "on", why ? why : "");
+            }
         }
         c->pre_steps.push_back(B.step(i, true));
     }
@@ -905,6 +912,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "persist") == 0 && value >= 0 && value <= 2) { c->persist = value; return MFTB200_OK; }
+    if (strcmp(key, "tma_store") == 0) { c->tma_store = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "prog_timing") == 0) { c->prog.timing = c->prog_full.timing = value ? c->prog_timing : nullptr; return MFTB200_OK; }
     if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
