@@ -101,6 +101,16 @@ __device__ __forceinline__ void epilogue4(const ConvEpi& e, float4 v, const floa
     } else if constexpr (MODE == EPI_F32) {
         v.x = fmaxf(v.x * e.scale, relu_lo); v.y = fmaxf(v.y * e.scale, relu_lo);
         v.z = fmaxf(v.z * e.scale, relu_lo); v.w = fmaxf(v.w * e.scale, relu_lo);
+        if (e.out16 != nullptr) {          // same epilogue (64-bit addressing, scale), result stored as fp16: the correlation volume
+            __half* o = e.out16 + pix * e.out16_stride + e.out16_coff + col;
+            if (full && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+                *reinterpret_cast<uint2*>(o) = pack_half4(v.x, v.y, v.z, v.w);
+            } else {
+                const float a[4] = {v.x, v.y, v.z, v.w};
+                for (int j = 0; j < 4 && col + j < e.n_valid; ++j) o[j] = __float2half_rn(a[j]);
+            }
+            return;
+        }
         float* o = e.out32 + pix * e.out32_stride + e.out32_coff + col;
         if (full && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
             *reinterpret_cast<float4*>(o) = v;

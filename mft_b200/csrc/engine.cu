@@ -70,7 +70,8 @@ struct mftb200_ctx {
     int* slot_table = nullptr;
     __half *F1 = nullptr, *F2 = nullptr, *corr16 = nullptr, *flowpatch = nullptr, *c1buf = nullptr, *cf = nullptr,
            *f1buf = nullptr, *X = nullptr, *fhbuf = nullptr, *oupack = nullptr;
-    float *corr[4] = {nullptr, nullptr, nullptr, nullptr}, *h32 = nullptr, *z32 = nullptr, *coords1 = nullptr,
+    __half* corr[4] = {nullptr, nullptr, nullptr, nullptr};      // correlation pyramid, fp16
+    float *h32 = nullptr, *z32 = nullptr, *coords1 = nullptr,
           *delta32 = nullptr, *mask32 = nullptr, *ou32 = nullptr, *out = nullptr;
     size_t corr_bytes[4] = {0, 0, 0, 0};
 
@@ -99,7 +100,6 @@ struct mftb200_ctx {
     // 1 = one launch per iteration (default), 2 = ONE launch for all iterations with the pyramid lookup as tiles of the
     // program (correct, but the lookup is latency-bound on 8 warps per SM: slower, kept as an option under test)
     int persist = 1;
-    int tma_store = 1;                     // correlation volume written with bulk tensor stores (next configure)
     ConvProgram prog, prog_full, prog_heads;   // prog_heads: mask head || OU head after the last iteration
     bool prog_heads_ok = false;
     int fz_ou_pack = -1, fz_upsample = -1;
@@ -319,12 +319,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         const int i = B.conv(-1, in, mp, 1, t1, 256, EPI_F32, 1, 128, c->F2, npx, npx);
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
-            e.scale = 0.0625f; e.out32 = c->corr[0]; e.out32_stride = npx; e.out32_coff = 0; e.n_valid = npx;
-            c->plans[i].mode = EPI_F32;
-            if (c->tma_store) {                                    // else: per-thread stores
-                const char* why = conv_plan_enable_tma_store(&c->plans[i], static_cast<long>(mp) * npx);
-                if (getenv("MFTB200_DEBUG")) fprintf(stderr, "mft_b200: correlation bulk-store epilogue %s%s\n", why ? "off: " : "on", why ? why : "");
-            }
+            e.scale = 0.0625f; e.out16 = c->corr[0]; e.out16_stride = npx; e.out16_coff = 0; e.n_valid = npx;
         }
         c->pre_steps.push_back(B.step(i, true));
     }
@@ -696,8 +691,8 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     chk(c->F2 = c->dalloc<__half>(M * 256));
     int hl = c->h, wl = c->w;
     for (int l = 0; l < 4; ++l) {
-        c->corr_bytes[l] = M * hl * wl * sizeof(float);
-        chk(c->corr[l] = c->dalloc<float>(M * hl * wl));
+        c->corr_bytes[l] = M * hl * wl * sizeof(__half);
+        chk(c->corr[l] = c->dalloc<__half>(M * hl * wl));
         hl /= 2; wl /= 2;
     }
     chk(c->corr16 = c->dalloc<__half>(M * 328));
@@ -797,8 +792,8 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
         cudaEventRecord(c->ev_start, s);
         cudaStreamWaitEvent(c->gs[1][0], c->ev_start, 0);
     }
-    int r = run_steps_groups(c, c->pre_steps, groups, n_groups);
     const bool layered = n_groups != 1 || c->conv_impl || c->persist == 0;
+    int r = run_steps_groups(c, c->pre_steps, groups, n_groups);
     if (!layered && c->persist == 2 && c->prog_full_ok && c->iters <= 64 && r == MFTB200_OK) {
         // all iterations in ONE launch: lookup + 11 convolutions per iteration as tiles of one dataflow program
         c->cur_group = 0; c->cur_b0 = 0; c->cur_pairs = n_pairs;
@@ -912,8 +907,11 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     if (strcmp(key, "iters") == 0 && value >= 1) { c->iters = value; return MFTB200_OK; }
     if (strcmp(key, "split_pairs") == 0) { c->split_pairs = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "persist") == 0 && value >= 0 && value <= 2) { c->persist = value; return MFTB200_OK; }
-    if (strcmp(key, "tma_store") == 0) { c->tma_store = value ? 1 : 0; return MFTB200_OK; }
-    if (strcmp(key, "prog_timing") == 0) { c->prog.timing = c->prog_full.timing = value ? c->prog_timing : nullptr; return MFTB200_OK; }
+    if (strcmp(key, "prog_timing") == 0) {           // 1: iteration programs, 2: heads program
+        c->prog.timing = c->prog_full.timing = value == 1 ? c->prog_timing : nullptr;
+        c->prog_heads.timing = value == 2 ? c->prog_timing : nullptr;
+        return MFTB200_OK;
+    }
     if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
@@ -1042,6 +1040,8 @@ int mftb200_conv2d_bench2(const uint16_t* x_dev, int B, int H, int W, int pitch,
     p.e.bias = bias_dev; p.e.scale = 1.0f; p.e.relu = relu; p.e.n_valid = cout_pad;
     p.e.out32 = out_dev; p.e.out32_stride = cout_pad; p.e.out32_coff = 0; p.e.err_flag = flag;
     p.e.timing = timing_dev;
+    // GEMM views (one-row "images") with a dense fp32 output go out through the bulk-tensor-store epilogue
+    if (H == 1 && kh == 1 && kw == 1 && stride == 1 && impl == 0) conv_plan_enable_tma_store(&p, static_cast<long>(B) * W);
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);

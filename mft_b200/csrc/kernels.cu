@@ -428,7 +428,7 @@ void launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
 // correlation pyramid pooling (core/corr.py:26-28): avg_pool2d(2, stride 2), floor sizes
 // ==========================================================================================
 __global__ void __launch_bounds__(256)
-corr_pool_kernel(const float* __restrict__ L0, float* __restrict__ L1, float* __restrict__ L2, float* __restrict__ L3,
+corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half* __restrict__ L2, __half* __restrict__ L3,
                  int h, int w) {
     pdl_enter();
     extern __shared__ float sm[];
@@ -436,31 +436,33 @@ corr_pool_kernel(const float* __restrict__ L0, float* __restrict__ L1, float* __
     float* s1 = sm;
     float* s2 = sm + h1 * w1;
     const long row = blockIdx.x;
-    const float* src = L0 + row * h * w;
+    const __half* src = L0 + row * h * w;
+    // every level is the fp32 average of the level above as it is STORED (fp16), rounded once: what avg_pool2d of the
+    // stored volume gives (core/corr.py:26-28)
     for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
         const int y = i / w1, x = i % w1;
-        const float* q = src + (2 * y) * w + 2 * x;
-        const float v = (((q[0] + q[1]) + q[w]) + q[w + 1]) * 0.25f;
-        s1[i] = v;
-        L1[row * h1 * w1 + i] = v;
+        const __half* q = src + (2 * y) * w + 2 * x;
+        const __half r = __float2half_rn((((__half2float(q[0]) + __half2float(q[1])) + __half2float(q[w])) + __half2float(q[w + 1])) * 0.25f);
+        s1[i] = __half2float(r);
+        L1[row * h1 * w1 + i] = r;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
         const int y = i / w2, x = i % w2;
         const float* q = s1 + (2 * y) * w1 + 2 * x;
-        const float v = (((q[0] + q[1]) + q[w1]) + q[w1 + 1]) * 0.25f;
-        s2[i] = v;
-        L2[row * h2 * w2 + i] = v;
+        const __half r = __float2half_rn((((q[0] + q[1]) + q[w1]) + q[w1 + 1]) * 0.25f);
+        s2[i] = __half2float(r);
+        L2[row * h2 * w2 + i] = r;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < h3 * w3; i += blockDim.x) {
         const int y = i / w3, x = i % w3;
         const float* q = s2 + (2 * y) * w2 + 2 * x;
-        L3[row * h3 * w3 + i] = (((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f;
+        L3[row * h3 * w3 + i] = __float2half_rn((((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f);
     }
 }
 
-void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long rows, int h, int w, cudaStream_t stream) {
+void launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (static_cast<size_t>(h / 2) * (w / 2) + static_cast<size_t>(h / 4) * (w / 4));
     static bool attr = false;
     if (!attr) {

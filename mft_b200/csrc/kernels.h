@@ -65,10 +65,10 @@ struct PairSetup {
 void launch_pair_setup(const PairSetup& a, cudaStream_t stream);
 
 // 2x2 average pooling of the correlation volume over the target dims: L0 [rows][h*w] -> L1..L3.
-void launch_corr_pool(const float* L0, float* L1, float* L2, float* L3, long rows, int h, int w, cudaStream_t stream);
+void launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream);
 
 struct LookupArgs {
-    const float* lvl[4];             // pyramid levels [pair*Npx + n][h_l*w_l]
+    const __half* lvl[4];            // pyramid levels [pair*Npx + n][h_l*w_l], fp16
     const float* coords1;            // [pair][Npx][2]
     __half* corr16;                  // [pair*Npx][328]  (324 used)
     __half* flowpatch16;             // [pair*Npx][104]  (98 used): 7x7x2 neighbourhood of the flow

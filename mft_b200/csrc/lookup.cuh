@@ -90,13 +90,13 @@ __device__ __forceinline__ void lookup_gather(const LookupArgs& a, const LookupL
         px.wE[l] = __shfl_sync(0xffffffffu, my_wE, l);
         px.wS[l] = __shfl_sync(0xffffffffu, my_wS, l);
         const int X0 = __shfl_sync(0xffffffffu, my_X0, l), Y0 = __shfl_sync(0xffffffffu, my_Y0, l);
-        const float* base = a.lvl[l] + pp * static_cast<long>(hl * wl);
+        const __half* base = a.lvl[l] + pp * static_cast<long>(hl * wl);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k < 3 || lane < kLkWin * kLkWin - 96) {
                 const unsigned gx = static_cast<unsigned>(X0 + t.ex[k]), gy = static_cast<unsigned>(Y0 + t.ey[k]);
                 float v = 0.0f;
-                if (gx < static_cast<unsigned>(wl) && gy < static_cast<unsigned>(hl)) v = __ldg(base + gy * wl + gx);
+                if (gx < static_cast<unsigned>(wl) && gy < static_cast<unsigned>(hl)) v = __half2float(__ldg(base + gy * wl + gx));
                 win[l * kLkLevelFloats + lane + 32 * k] = v;
             }
         }

@@ -198,3 +198,21 @@ def test_warp_forward_splat_kernel(size):
     # a zero flow splats every pixel onto itself (the reference gives the last row / column zero weight)
     ident = FlowOUTrackingResult.identity((H, W), device='cuda')
     assert np.abs(ident.warp_forward(img)[:-1, :-1] - img[:-1, :-1]).max() < 1e-6
+
+
+def test_gemm_view_bulk_store_epilogue():
+    """One-row geometry (a GEMM: rows x cin @ cin x cout): the fp32 output leaves through 32 x 32 cp.async.bulk.tensor
+    stores (3-D map, clipped per batch entry) instead of per-thread stores -- ragged row and column counts included."""
+    from mft_b200 import engine as E, weights as WT
+    g = torch.Generator().manual_seed(3)
+    B, rows, cin, cout = 3, 300, 200, 160
+    x = torch.randn(B, 1, rows, 200, generator=g).half().cuda()
+    w = (torch.randn(cout, cin, 1, 1, generator=g) / np.sqrt(cin)).half().float()
+    b = torch.randn(cout, generator=g)
+    w16, bias, cout_pad, ktot, _ = WT._pack(w, b, cout_pad=256)
+    out = E.conv2d_test(x, torch.from_numpy(w16.view(np.float16)).cuda(), torch.from_numpy(bias).cuda(), cin, cout_pad, 256, 1, 1, 1,
+                        True, 0)
+    ref = torch.relu(x[:, 0].float() @ w[:, :, 0, 0].t().cuda() + b.cuda())
+    assert tuple(out.shape) == (B, 1, rows, cout_pad)
+    assert (out[:, 0, :, :cout] - ref).abs().max().item() < 2e-3
+    assert out[:, 0, :, cout:].abs().max().item() == 0

@@ -70,7 +70,7 @@ def test_stage_boundaries_128(tag, request):
     eng.refine([0], [1])
     eng.check_device()
     for lvl, n in enumerate((256, 64, 16, 4)):
-        c = eng.debug_buffer(f'corr_l{lvl}', torch.float32, (npx, n)).cpu()
+        c = eng.debug_buffer(f'corr_l{lvl}', torch.float16, (npx, n)).float().cpu()
         assert _rel(c, taps['pyramid'][lvl].reshape(npx, n)) < 0.005, lvl
     it0 = taps['iters'][0]
     c16 = eng.debug_buffer('corr16', torch.float16, (npx, 328)).float().cpu()
