@@ -14,7 +14,7 @@ torch.backends.cudnn.allow_tf32 = False
 LAYERS = {   # name: (cin, cout, kh, kw, n_tile)
     'convc1': (324, 256, 1, 1, 256), 'convc2': (256, 192, 3, 3, 192), 'convf1': (98, 128, 1, 1, 128),
     'convf2': (128, 64, 3, 3, 64), 'convm': (256, 126, 3, 3, 128), 'gru_zr': (384, 256, 1, 5, 256),
-    'gru_q': (384, 128, 5, 1, 128), 'fh1': (128, 256, 3, 3, 256), 'fh2': (256, 2, 3, 3, 16), 'ou1': (712, 256, 3, 3, 256),
+    'gru_q': (384, 128, 5, 1, 128), 'fh1': (128, 256, 3, 3, 256), 'fh2': (256, 2, 3, 3, 16), 'ou1': (712, 256, 3, 3, 256), 'corr': (256, 4096, 1, 1, 256),
 }
 
 
