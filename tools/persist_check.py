@@ -71,6 +71,7 @@ out = eng.refine(lefts, rights)
 t = eng.debug_buffer('prog_timing', torch.int64, (256, 16)).cpu().numpy().astype(float)
 t = t[t[:, 4] > 0]
 us = lambda c: c / 1.965e3
+print(f'{len(t)} CTAs; MMA warp span min {us(t[:, 0].min()):.1f} / max {us(t[:, 0].max()):.1f} us; busy (not waiting for tickets) min {us((t[:, 0] - t[:, 1]).min()):.1f} / mean {us((t[:, 0] - t[:, 1]).mean()):.1f} / max {us((t[:, 0] - t[:, 1]).max()):.1f} us; tiles min {t[:, 4].min():.0f} / max {t[:, 4].max():.0f}')
 print(f'{len(t)} CTAs; MMA warp: {us(t[:, 0].mean()):.1f} us in the launch, {t[:, 4].mean():.1f} tiles, {t[:, 5].mean():.0f} stages per CTA')
 print(f'   MMA warp waits: ticket {us(t[:, 1].mean()):.1f} us, accumulator free {us(t[:, 2].mean()):.1f} us, '
       f'operands {us(t[:, 3].mean()):.1f} us ({t[:, 3].sum() / t[:, 5].sum():.0f} cycles per stage); '
