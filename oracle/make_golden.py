@@ -12,8 +12,11 @@ Files
   raft_real_128.npz     same pairs with the shipped checkpoint (needs the checkpoint at test time)
   chain_select.npz      MFT.track's chaining + selection + invalid mask through the reference's own
                         tracker class around a replay flower (synthetic flows incl. overflow/ties/all-occluded/OOB)
+  raft_seeded_pad.npz   seeded weights, demo frames 0,2 at 131x140 (replicate pad 2|3 rows, 2|2 columns, then unpad)
   warp_forward.npz      FlowOUTrackingResult.warp_forward (bilinear forward splat, results.py:190-248) of a random image
                         through a random flow with end points outside the grid, with and without mask / border
+  point_queries.npz     FlowOUTrackingResult.chain / warp_backward / warp_forward_points / sample / invalid_mask and
+                        point_tracking.convert_to_point_tracking on a random result, queries inside / on the border / outside
   track_real_128.npz    10 demo frames at 128x128, deltas [inf,1,2,4,8], shipped checkpoint: the
                         reference tracker's per-frame results (full field for 3 frames + per-frame sums)
 """
@@ -62,6 +65,48 @@ def warp_forward_case():
     res = RefRes(torch.from_numpy(flow), torch.zeros(1, H, W), torch.zeros(1, H, W))
     return dict(flow=flow, img=img, mask=mask, out_plain=res.warp_forward(img).astype(np.float32),
                 out_mask=res.warp_forward(img, mask=mask, border=-1.0).astype(np.float32))
+
+
+def padded_case():
+    """One pair at 131x140 (pad 5 -> 2|3 rows, 4 -> 2|2 columns: InputPadder, core/utils/utils.py:9-24) through the reference's
+    compute_flow with the seeded weights: pins replicate padding + unpadding, incl. the odd split."""
+    import cv2
+    Wseed = O.seeded_weights(0)
+    seeded = R.build_reference_model(Wseed)
+    fr = [cv2.resize(f, (140, 131), interpolation=cv2.INTER_AREA) for f in R.demo_frames(3, size=(256, 256))]
+    g = raft_pairs(seeded, {0: fr[0], 2: fr[2]}, [(0, 2)], 'pad')
+    g['frames'] = np.stack([fr[0], fr[2]])
+    return g
+
+
+def point_query_case():
+    """FlowOUTrackingResult geometry + point_tracking.convert_to_point_tracking of the unmodified reference (results.py:87-188,
+    250-265; point_tracking.py:6-27) on a random result: queries on pixel centres, between them, on the border and outside."""
+    R._import_reference()
+    from MFT.results import FlowOUTrackingResult as RefRes
+    from MFT.point_tracking import convert_to_point_tracking
+    rng = np.random.default_rng(99)
+    H, W = 36, 52
+    flow = (rng.standard_normal((2, H, W)) * 5).astype(np.float32)
+    flow[:, :3, :] -= 20
+    flow[:, :, -4:] += 25           # end points outside the image
+    occ = rng.uniform(0, 1, (1, H, W)).astype(np.float32)
+    sigma = rng.uniform(0.1, 4, (1, H, W)).astype(np.float32)
+    other = (rng.standard_normal((2, H, W)) * 3).astype(np.float32)
+    img = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
+    q = np.concatenate([rng.uniform([0, 0], [W - 1, H - 1], (40, 2)),
+                        np.array([[0, 0], [W - 1, H - 1], [W - 1, 0], [0, H - 1], [7, 11], [W - 1.5, H - 1.25]]),
+                        np.array([[-0.5, 3.0], [W - 0.5, 3.0], [5.0, -0.75], [5.0, H - 0.25], [-3.0, -3.0], [W + 4.0, H + 9.0]]),
+                        ]).astype(np.float32)
+    res = RefRes(torch.from_numpy(flow), torch.from_numpy(occ), torch.from_numpy(sigma))
+    qt = torch.from_numpy(q)
+    sf, so, ss = res.sample(qt)
+    pc, po = convert_to_point_tracking(res, qt)
+    return dict(flow=flow, occlusion=occ, sigma=sigma, other=other, img=img, queries=q,
+                warped_points=_np(res.warp_forward_points(qt)), sample_flow=_np(sf), sample_occlusion=_np(so),
+                sample_sigma=_np(ss), pt_coords=np.asarray(pc, np.float32), pt_occlusion=np.asarray(po, np.float32),
+                chained=_np(res.chain(torch.from_numpy(other))), warped_img=_np(res.warp_backward(torch.from_numpy(img))),
+                invalid=res.invalid_mask().numpy().astype(np.bool_))
 
 
 def chain_select_case(rng, H, W, K, thr):
@@ -187,6 +232,8 @@ def main():
     g['thr'] = np.array(0.02, np.float32)
     np.savez_compressed(os.path.join(OUT, 'chain_select.npz'), **g)
     np.savez_compressed(os.path.join(OUT, 'warp_forward.npz'), **warp_forward_case())
+    np.savez_compressed(os.path.join(OUT, 'point_queries.npz'), **point_query_case())
+    np.savez_compressed(os.path.join(OUT, 'raft_seeded_pad.npz'), **padded_case())
 
     # --- short real tracking run ---------------------------------------------------------------
     deltas = [np.inf, 1, 2, 4, 8]

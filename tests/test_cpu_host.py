@@ -314,3 +314,25 @@ def test_device_flow_cache_protocol_on_cpu_tensors():
     h = DeviceFlowCache(dtype=torch.float16, device='cpu')
     h.write(0, 1, torch.full((2, H, W), 1.5), torch.zeros(1, H, W), torch.ones(1, H, W))
     assert h.bytes == one // 2 and h.read(0, 1)[0].dtype == torch.float32 and h.read(0, 1)[0].mean() == 1.5
+
+
+def test_point_queries_cpu_paths_match_reference_golden():
+    """Result geometry + convert_to_point_tracking on CPU tensors (what callers hold after track()) against vectors recorded
+    from the unmodified reference (results.py:87-188,250-265; point_tracking.py:6-27): queries inside, on the border, outside."""
+    from conftest import golden
+    from mft_b200.point_tracking import convert_to_point_tracking
+    from mft_b200.results import FlowOUTrackingResult
+    g = golden('point_queries.npz')
+    res = FlowOUTrackingResult(torch.from_numpy(g['flow']), torch.from_numpy(g['occlusion']), torch.from_numpy(g['sigma']))
+    q = torch.from_numpy(g['queries'])
+    assert np.abs(res.warp_forward_points(q).numpy() - g['warped_points']).max() < 1e-4
+    f, o, s = res.sample(q)
+    assert tuple(f.shape) == g['sample_flow'].shape and tuple(o.shape) == g['sample_occlusion'].shape
+    assert np.abs(f.numpy() - g['sample_flow']).max() < 1e-4
+    assert np.abs(o.numpy() - g['sample_occlusion']).max() < 1e-5 and np.abs(s.numpy() - g['sample_sigma']).max() < 1e-5
+    pc, po = convert_to_point_tracking(res, g['queries'])
+    assert pc.shape == g['pt_coords'].shape and po.shape == g['pt_occlusion'].shape and po.dtype == np.float32
+    assert np.abs(pc - g['pt_coords']).max() < 1e-4 and np.abs(po - g['pt_occlusion']).max() < 1e-5
+    assert np.abs(res.chain(torch.from_numpy(g['other'])).numpy() - g['chained']).max() < 1e-4
+    assert np.abs(res.warp_backward(torch.from_numpy(g['img'])).numpy() - g['warped_img']).max() < 1e-5
+    assert np.array_equal(res.invalid_mask().numpy(), g['invalid'])

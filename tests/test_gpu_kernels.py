@@ -127,6 +127,28 @@ def test_warp_backward_chain_and_points_bit_exact():
     assert np.array_equal(res_cpu.invalid_mask().numpy(), res.invalid_mask().cpu().numpy())
 
 
+def test_point_queries_vs_reference_golden():
+    """Device point queries (one launch for coordinates + occlusion) and result geometry against vectors recorded from the
+    unmodified reference (results.py:87-188; point_tracking.py:6-27); fp32 interpolation round-off only."""
+    from mft_b200.point_tracking import convert_to_point_tracking
+    from mft_b200.results import FlowOUTrackingResult
+    g = golden('point_queries.npz')
+    packed = torch.from_numpy(np.concatenate([g['flow'], g['occlusion'], g['sigma']])).cuda()
+    res = FlowOUTrackingResult.from_packed(packed)
+    q = torch.from_numpy(g['queries']).cuda()
+    assert np.abs(res.warp_forward_points(q).cpu().numpy() - g['warped_points']).max() < 1e-4
+    f, o, s = res.sample(q)
+    assert np.abs(f.cpu().numpy() - g['sample_flow']).max() < 1e-4
+    assert np.abs(o.cpu().numpy() - g['sample_occlusion']).max() < 1e-5
+    assert np.abs(s.cpu().numpy() - g['sample_sigma']).max() < 1e-5
+    pc, po = convert_to_point_tracking(res, g['queries'])           # host queries, device result
+    assert isinstance(pc, np.ndarray) and pc.shape == g['pt_coords'].shape and po.shape == g['pt_occlusion'].shape
+    assert np.abs(pc - g['pt_coords']).max() < 1e-4 and np.abs(po - g['pt_occlusion']).max() < 1e-5
+    assert np.abs(res.chain(torch.from_numpy(g['other']).cuda()).cpu().numpy() - g['chained']).max() < 1e-4
+    assert np.abs(res.warp_backward(torch.from_numpy(g['img']).cuda()).cpu().numpy() - g['warped_img']).max() < 1e-5
+    assert np.array_equal(res.invalid_mask().cpu().numpy(), g['invalid'])
+
+
 CONV_CASES = [
     # cin, cout, kh, kw, stride, H, W, B, n_tile
     (64, 64, 1, 1, 1, 8, 16, 1, 64), (128, 64, 1, 1, 1, 8, 16, 1, 64), (64, 64, 3, 3, 1, 16, 16, 1, 64),

@@ -130,6 +130,18 @@ def test_padding_and_ragged_tiles_seeded(size, seeded_weights):
     assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
 
 
+def test_padded_size_vs_reference_golden(seeded_weights):
+    """131x140 (odd replicate pad 2|3 rows) against the vectors recorded from the unmodified reference."""
+    g = golden('raft_seeded_pad.npz')
+    H, Wd = 131, 140
+    eng = _engine(seeded_weights, H, Wd)
+    eng.encode_frame(g['frames'][0], 0); eng.encode_frame(g['frames'][1], 1)
+    out = eng.refine([0], [1])
+    eng.check_device()
+    st = _flow_stats(out[0], torch.from_numpy(g['flow_0_2']), torch.from_numpy(g['occ_0_2']), torch.from_numpy(g['sigma_0_2']))
+    assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
+
+
 def test_batched_equals_single_pair(seeded_weights):
     """A pair's result must not depend on what else is in the batch (bit-exact)."""
     from mft_b200.synth import synthetic_video

@@ -42,6 +42,14 @@ def test_raft_128(tag, request):
     _check_pair(g, 0, 8, W, frames)
 
 
+def test_raft_padded_size_seeded(seeded_weights):
+    """131x140: InputPadder's replicate pad (2|3 rows, 2|2 columns) and the unpad (core/utils/utils.py:9-24, MFT/raft.py:47-58)."""
+    g = golden('raft_seeded_pad.npz')
+    assert tuple(O.pad_amounts(131, 140)) == (2, 2, 2, 3)                 # (left, right, top, bottom)
+    assert g['flow_0_2'].shape == (2, 131, 140)
+    _check_pair(g, 0, 2, seeded_weights, {0: g['frames'][0], 2: g['frames'][1]})
+
+
 def test_chain_select_vs_reference_tracker():
     """Chaining + selection + invalid mask, against MFT.track itself fed with recorded flows."""
     g = golden('chain_select.npz')
@@ -142,3 +150,19 @@ def test_warp_forward_matches_reference():
     g = golden('warp_forward.npz')
     assert np.abs(O.warp_forward(g['flow'], g['img']) - g['out_plain']).max() < 1e-6
     assert np.abs(O.warp_forward(g['flow'], g['img'], g['mask'], -1.0) - g['out_mask']).max() < 1e-6
+
+
+def test_point_queries_match_reference():
+    """Point queries: the oracle's bilinear sampler / chain against FlowOUTrackingResult.sample /
+    warp_forward_points / chain / warp_backward of the unmodified reference, incl. queries on the border and outside."""
+    g = golden('point_queries.npz')
+    packed = np.concatenate([g['flow'], g['occlusion'], g['sigma']])
+    q = g['queries']
+    s = O.bilinear_zero(packed, q[:, 0], q[:, 1], via_mul=True)
+    assert np.abs(s[:2] - g['sample_flow']).max() < 1e-4
+    assert np.abs(s[2:3] - g['sample_occlusion']).max() < 1e-5 and np.abs(s[3:4] - g['sample_sigma']).max() < 1e-5
+    assert np.abs((q + s[:2].T) - g['warped_points']).max() < 1e-4
+    assert np.abs(s[2] - g['pt_occlusion']).max() < 1e-5 and np.abs((q + s[:2].T) - g['pt_coords']).max() < 1e-4
+    z = np.zeros_like(g['occlusion'])
+    wf, _, _ = O.chain((g['flow'], g['occlusion'], g['sigma']), (g['other'], z, z))
+    assert np.abs(wf - g['chained']).max() < 1e-4
