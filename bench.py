@@ -258,6 +258,9 @@ def run_ours(args):
     # ---- reach the steady state -------------------------------------------------------------------
     tracker.init(frames[0])
     eng = tracker.engine
+    for kv in filter(None, os.environ.get('BENCH_ENGINE_OPTIONS', '').split(',')):      # A/B runs, e.g. defer_context=0
+        k, v = kv.split('=')
+        eng.set_option(k.strip(), int(v))
     t = 1
     for _ in range(STEADY):
         tracker.track(dev_frames[t], device_result=True)

@@ -72,7 +72,7 @@ struct mftb200_ctx {
            *f1buf = nullptr, *X = nullptr, *fhbuf = nullptr, *oupack = nullptr;
     __half* corr[4] = {nullptr, nullptr, nullptr, nullptr};      // correlation pyramid, fp16
     float *h32 = nullptr, *z32 = nullptr, *coords1 = nullptr,
-          *delta32 = nullptr, *mask32 = nullptr, *ou32 = nullptr, *out = nullptr;
+          *delta32 = nullptr, *mask32 = nullptr, *ou32 = nullptr;
     size_t corr_bytes[4] = {0, 0, 0, 0};
 
     std::vector<ConvPlan> plans;
@@ -112,6 +112,18 @@ struct mftb200_ctx {
     std::vector<cudaEvent_t> prof_events;   // pairs
     std::vector<int> prof_kinds, prof_tags;
     int cur_slot = 0, cur_pairs = 0;       // cur_pairs / cur_b0: size and first pair of the sub-batch being enqueued
+    float* out_cur = nullptr;              // where the upsampling kernel writes: the caller's buffer of the current refine
+    // Deferred context encoder.  cnet(t) is only read when frame t is the LEFT image of a pair, i.e. from the next frame
+    // on, so it does not have to sit on frame t's critical path: encode_frame runs fnet (+ cnet's first convolution, which
+    // shares the patch matrix with fnet) and parks the rest of cnet; raft_refine enqueues it on `ctx_stream` behind its
+    // own work, where it overlaps chain+select, the result's device->host copy and the caller's time between frames.
+    // Any call that needs the context earlier (the slot as a left image, a second encode, a debug read) flushes it first.
+    int defer_context = 1;
+    int pending_ctx_slot = -1;
+    cudaStream_t ctx_stream = nullptr, last_main = nullptr;
+    cudaEvent_t ev_ctx_fork = nullptr, ev_ctx_first = nullptr, ev_ctx_go = nullptr, ev_ctx_done = nullptr;
+    bool ctx_done_valid = false;
+    std::vector<Step> enc_f_steps, ctx_first_steps, ctx_rest_steps;
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -136,6 +148,9 @@ struct mftb200_ctx {
         plans.clear();
         plan_layer.clear();
         enc_steps.clear(); pre_steps.clear(); iter_steps.clear(); final_steps.clear();
+        enc_f_steps.clear(); ctx_first_steps.clear(); ctx_rest_steps.clear();
+        pending_ctx_slot = -1;
+        ctx_done_valid = false;
         configured = false;
     }
 };
@@ -481,7 +496,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     Fz.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
         UpsampleArgs a{cc->mask32 + o * 576, cc->coords1 + o * 2, cc->ou32 + o * 4,
-                       cc->out + static_cast<size_t>(cc->cur_b0) * 4 * cc->H * cc->W, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
+                       cc->out_cur + static_cast<size_t>(cc->cur_b0) * 4 * cc->H * cc->W, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
                        cc->pad_l, cc->pad_t};
         launch_upsample(a, s);
         cc->launches++;
@@ -572,6 +587,29 @@ int run_steps_groups(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cons
     return MFTB200_OK;
 }
 
+// Enqueues the parked part of the context encoder on ctx_stream, ordered after everything queued on `after` so far.
+// wait_on != nullptr: that stream then waits for the context (it is about to read it).
+int flush_context(mftb200_ctx* c, cudaStream_t after, cudaStream_t wait_on) {
+    if (c->pending_ctx_slot >= 0) {
+        const int keep = c->cur_slot;
+        c->cur_slot = c->pending_ctx_slot;
+        c->pending_ctx_slot = -1;
+        cudaEventRecord(c->ev_ctx_go, after);
+        cudaStreamWaitEvent(c->ctx_stream, c->ev_ctx_go, 0);
+        for (auto& st : c->ctx_rest_steps) {
+            if (const char* e = st.fn(c, c->ctx_stream)) {
+                c->cur_slot = keep;
+                return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+            }
+        }
+        cudaEventRecord(c->ev_ctx_done, c->ctx_stream);
+        c->ctx_done_valid = true;
+        c->cur_slot = keep;
+    }
+    if (wait_on != nullptr && c->ctx_done_valid) cudaStreamWaitEvent(wait_on, c->ev_ctx_done, 0);
+    return MFTB200_OK;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -612,12 +650,18 @@ int mftb200_create(mftb200_ctx** out) {
     }
     cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->ctx_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_ctx_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_ctx_first, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_ctx_go, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_ctx_done, cudaEventDisableTiming);
     *out = c;
     return MFTB200_OK;
 }
 
 void mftb200_destroy(mftb200_ctx* c) {
     if (!c) return;
+    cudaDeviceSynchronize();          // the context stream may still be running
     c->free_workspace();
     for (auto& L : c->layers) {
         cudaFree(L.w);
@@ -633,6 +677,9 @@ void mftb200_destroy(mftb200_ctx* c) {
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->ctx_stream) cudaStreamDestroy(c->ctx_stream);
+    for (cudaEvent_t ev : {c->ev_ctx_fork, c->ev_ctx_first, c->ev_ctx_go, c->ev_ctx_done})
+        if (ev) cudaEventDestroy(ev);
     delete c;
 }
 
@@ -709,7 +756,6 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     chk(c->delta32 = c->dalloc<float>(M * 2));
     chk(c->mask32 = c->dalloc<float>(M * 576));
     chk(c->ou32 = c->dalloc<float>(M * 4));
-    chk(c->out = c->dalloc<float>(static_cast<size_t>(max_pairs) * 4 * H * W));
     if (!ok) {
         c->free_workspace();
         return c->fail(MFTB200_ERR_CUDA, "configure: out of device memory");
@@ -735,6 +781,11 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
             if (ci < csteps.size()) c->enc_steps.push_back(csteps[ci++]);
         }
         c->enc_steps.push_back(sync_step(2));
+        // the same launches split for the deferred-context schedule (see mftb200_ctx::defer_context)
+        c->enc_f_steps.push_back(c->enc_steps[0]);
+        for (auto& st : fsteps) c->enc_f_steps.push_back(st);
+        c->ctx_first_steps.push_back(csteps[0]);
+        for (size_t i = 1; i < csteps.size(); ++i) c->ctx_rest_steps.push_back(csteps[i]);
     }
     if (!e) e = build_refine(c, B);
     if (e) {
@@ -752,12 +803,38 @@ int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int 
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "encode_frame: not configured");
     if (!bgr || slot < 0 || slot >= c->n_slots) return c->fail(MFTB200_ERR_ARG, "encode_frame: bad slot %d", slot);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    c->last_main = s;
+    // a context still parked (two encodes without a refine in between) goes first: it reads cnet's activation buffers
+    if (int r = flush_context(c, s, nullptr)) return r;
     const size_t bytes = static_cast<size_t>(c->H) * c->W * 3;
     if (cudaMemcpyAsync(c->frame_u8, bgr, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s) !=
         cudaSuccess)
         return c->fail(MFTB200_ERR_CUDA, "encode_frame: frame copy failed");
     c->cur_slot = slot;
-    return run_steps(c, c->enc_steps, s);
+    if (!c->defer_context || c->profile) {
+        // everything queued on ctx_stream so far has to be done with cnet's buffers before the side stream reuses them
+        if (c->ctx_done_valid) cudaStreamWaitEvent(s, c->ev_ctx_done, 0);
+        return run_steps(c, c->enc_steps, s);
+    }
+    // fnet on the caller's stream; cnet's first convolution (shares the patch matrix) on ctx_stream, the rest parked
+    c->gs[0][0] = s;
+    c->cur_group = 0;
+    c->cur_b0 = 0;
+    int r = run_one(c, c->enc_f_steps[0]);                                  // frame -> patch matrix
+    if (r != MFTB200_OK) return r;
+    cudaEventRecord(c->ev_ctx_fork, s);
+    cudaStreamWaitEvent(c->ctx_stream, c->ev_ctx_fork, 0);
+    for (auto& st : c->ctx_first_steps)
+        if (const char* e = st.fn(c, c->ctx_stream)) return c->fail(MFTB200_ERR_CUDA, "launch failed: %s", e);
+    cudaEventRecord(c->ev_ctx_first, c->ctx_stream);
+    for (size_t i = 1; i < c->enc_f_steps.size(); ++i) {
+        r = run_one(c, c->enc_f_steps[i]);
+        if (r != MFTB200_OK) return r;
+    }
+    // the patch matrix is free again (and every context queued before this frame's is complete) once that convolution ran
+    cudaStreamWaitEvent(s, c->ev_ctx_first, 0);
+    c->pending_ctx_slot = slot;
+    return MFTB200_OK;
 }
 
 int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, const int* right_slots, float* out,
@@ -774,6 +851,17 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
         table[2 * p + 1] = right_slots[p];
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    c->last_main = s;
+    {   // the context of a left image must be complete; a parked one is enqueued now if this call reads it
+        bool need = false;
+        for (int p = 0; p < n_pairs; ++p) need = need || left_slots[p] == c->pending_ctx_slot;
+        if (need || c->profile) {
+            if (int r = flush_context(c, s, s)) return r;
+        } else if (c->ctx_done_valid) {
+            cudaStreamWaitEvent(s, c->ev_ctx_done, 0);
+        }
+    }
+    c->out_cur = out;
     // pageable source: the runtime stages the copy before returning, so `table` may go out of scope
     if (cudaMemcpyAsync(c->slot_table, table, sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, s) != cudaSuccess)
         return c->fail(MFTB200_ERR_CUDA, "raft_refine: slot table copy failed");
@@ -847,9 +935,8 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
     c->cur_b0 = 0;
     c->cur_pairs = n_pairs;
     if (r != MFTB200_OK) return r;
-    if (cudaMemcpyAsync(out, c->out, sizeof(float) * 4 * n_pairs * c->H * c->W, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-        return c->fail(MFTB200_ERR_CUDA, "raft_refine: output copy failed");
-    return MFTB200_OK;
+    // the parked context encoder of the newest frame runs behind this call's work (nothing here reads it)
+    return flush_context(c, s, nullptr);
 }
 
 int mftb200_chain_select(int K, const float* const* left, const float* right, float occlusion_threshold, int H, int W,
@@ -914,6 +1001,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     }
     if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "defer_context") == 0) { c->defer_context = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()
@@ -967,6 +1055,7 @@ int mftb200_profile_fetch(mftb200_ctx* c, double* ms_by_kind, long long* steps_b
 int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* bytes) {
     if (!c || !name || !ptr || !bytes) return MFTB200_ERR_ARG;
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "debug_buffer: not configured");
+    if (c->pending_ctx_slot >= 0 && c->last_main != nullptr) flush_context(c, c->last_main, c->last_main);
     const size_t npx = c->npx, M = npx * c->max_pairs;
     struct Ent { const char* n; void* p; size_t b; };
     const Ent tab[] = {
