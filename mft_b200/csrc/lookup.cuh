@@ -37,21 +37,24 @@ struct LookupLane {
 };
 
 __device__ __forceinline__ LookupLane lookup_lane_init(int lane) {
+    // e -> e + 32 is (ey + 3, ex + 2), o -> o + 32 is (i + 3, j + 5), tap -> tap + 16 is (ky + 2, kx + 2), each with one carry:
+    // cheaper than a division per entry (the tables are rebuilt for every pixel when a warp handles only one)
     LookupLane t;
+    int ey = (lane * 26) >> 8, ex = lane - ey * kLkWin;              // lane / 10, lane % 10 (exact for lane < 69)
+    int i = (lane * 57) >> 9, j = lane - i * 9;                        // lane / 9, lane % 9
+    const int tap = lane >> 1;
+    int ky = (tap * 37) >> 8, kx = tap - ky * 7;                       // tap / 7, tap % 7 (tap < 16)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int e = lane + 32 * k;
-        t.ey[k] = e / kLkWin;
-        t.ex[k] = e - t.ey[k] * kLkWin;
-        const int f = lane + 32 * k, tap = f >> 1;
-        t.fdy[k] = tap / 7 - 3;
-        t.fdx[k] = tap - (tap / 7) * 7 - 3;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int o = lane + 32 * k;
-        const int i = o / 9, j = o - i * 9;
-        t.woff[k] = j * kLkWin + i;
+        t.ex[k] = ex; t.ey[k] = ey;
+        t.fdx[k] = kx - 3; t.fdy[k] = ky - 3;
+        if (k < 3) t.woff[k] = j * kLkWin + i;
+        ex += 2; ey += 3;
+        if (ex >= kLkWin) { ex -= kLkWin; ++ey; }
+        j += 5; i += 3;
+        if (j >= 9) { j -= 9; ++i; }
+        kx += 2; ky += 2;
+        if (kx >= 7) { kx -= 7; ++ky; }
     }
     return t;
 }
@@ -91,13 +94,17 @@ __device__ __forceinline__ void lookup_gather(const LookupArgs& a, const LookupL
         px.wS[l] = __shfl_sync(0xffffffffu, my_wS, l);
         const int X0 = __shfl_sync(0xffffffffu, my_X0, l), Y0 = __shfl_sync(0xffffffffu, my_Y0, l);
         const __half* base = a.lvl[l] + pp * static_cast<long>(hl * wl);
+        asm volatile("" : "+l"(base));       // keep the row pointer in registers (else it is re-derived from pp for every tap)
+        // unconditional loads (taps outside the map read element 0 and are zeroed afterwards): the address of a predicated
+        // load is recomputed under its predicate, which tripled the integer work of this loop
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k < 3 || lane < kLkWin * kLkWin - 96) {
                 const unsigned gx = static_cast<unsigned>(X0 + t.ex[k]), gy = static_cast<unsigned>(Y0 + t.ey[k]);
-                float v = 0.0f;
-                if (gx < static_cast<unsigned>(wl) && gy < static_cast<unsigned>(hl)) v = __half2float(__ldg(base + gy * wl + gx));
-                win[l * kLkLevelFloats + lane + 32 * k] = v;
+                const bool inside = gx < static_cast<unsigned>(wl) && gy < static_cast<unsigned>(hl);
+                const unsigned off = inside ? gy * static_cast<unsigned>(wl) + gx : 0u;
+                const float v = __half2float(__ldg(base + off));
+                win[l * kLkLevelFloats + lane + 32 * k] = inside ? v : 0.0f;
             }
         }
         hl >>= 1; wl >>= 1;
@@ -134,10 +141,11 @@ __device__ __forceinline__ void lookup_emit(const LookupArgs& a, const LookupLan
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (k < 3 || lane < 104 - 96) {
-            float v = 0.0f;
             const unsigned xx = static_cast<unsigned>(x + t.fdx[k]), yy = static_cast<unsigned>(y + t.fdy[k]);
-            if ((k < 3 || lane < 98 - 96) && xx < static_cast<unsigned>(a.w) && yy < static_cast<unsigned>(a.h))
-                v = __ldcg(cbase + (yy * a.w + xx) * 2 + ch) - static_cast<float>(ch == 0 ? xx : yy);
+            const bool inside = (k < 3 || lane < 98 - 96) && xx < static_cast<unsigned>(a.w) && yy < static_cast<unsigned>(a.h);
+            const unsigned off = inside ? (yy * static_cast<unsigned>(a.w) + xx) * 2u + static_cast<unsigned>(ch) : 0u;
+            float v = __ldcg(cbase + off) - static_cast<float>(ch == 0 ? xx : yy);
+            v = inside ? v : 0.0f;
             fp[32 * k] = __float2half_rn(v);
         }
     }
