@@ -207,6 +207,22 @@ __device__ __forceinline__ void tile_epilogue(const ConvGeom& g, const ConvEpi& 
                 if (lane == 0) tma_store_wait_read<1>();          // the store that read this buffer two blocks ago is done
                 __syncwarp();
                 const float lo = e.relu ? 0.0f : -INFINITY;
+                if (e.out16 != nullptr) {
+                    // fp16 output (the correlation volume): 32 x 32 halves = 64-byte rows in TMA's 64-byte swizzle
+                    // (16-byte chunk index ^ address bits 7..8, i.e. ^ (row >> 1) & 3 in a 512-byte aligned buffer)
+                    uint8_t* hb = reinterpret_cast<uint8_t*>(buf);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float bia = e.bias != nullptr ? __ldg(e.bias + col0 + 8 * j + i) : 0.0f;
+                            w[i] = fmaxf((__uint_as_float(r[8 * j + i]) + bia) * e.scale, lo);
+                        }
+                        const uint2 lo4 = pack_half4(w[0], w[1], w[2], w[3]), hi4 = pack_half4(w[4], w[5], w[6], w[7]);
+                        *reinterpret_cast<uint4*>(hb + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(lo4.x, lo4.y, hi4.x, hi4.y);
+                    }
+                } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -217,6 +233,7 @@ __device__ __forceinline__ void tile_epilogue(const ConvGeom& g, const ConvEpi& 
                     v.z = fmaxf((__uint_as_float(r[4 * j + 2]) + bb.z) * e.scale, lo);
                     v.w = fmaxf((__uint_as_float(r[4 * j + 3]) + bb.w) * e.scale, lo);
                     *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+                }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -1432,19 +1449,25 @@ const char* conv_plan_enable_tma_store(ConvPlan* p, long rows) {
     p->e.tma_store = 0;
     if (p->mode != EPI_F32 || p->variant != 1) return "tma store: EPI_F32 plans of the 128-pixel kernel only";
     if (p->g.tile_h != 1 || p->g.H != 1) return "tma store: needs one-row tiles (GEMM view)";
-    if (p->e.out32 == nullptr || p->e.out32_coff != 0 || p->e.out32_stride % 4 != 0 || p->e.n_valid != p->e.out32_stride ||
-        (reinterpret_cast<uintptr_t>(p->e.out32) & 15) != 0)
+    const bool half = p->e.out16 != nullptr;           // fp16 output: 64-byte block rows, 64-byte swizzle
+    void* base = half ? static_cast<void*>(p->e.out16) : static_cast<void*>(p->e.out32);
+    const long stride = half ? p->e.out16_stride : p->e.out32_stride;
+    const int coff = half ? p->e.out16_coff : p->e.out32_coff;
+    const int esz = half ? 2 : 4;
+    if (base == nullptr || coff != 0 || (stride * esz) % 16 != 0 || p->e.n_valid != stride ||
+        (reinterpret_cast<uintptr_t>(base) & 15) != 0)
         return "tma store: output must be a dense, 16-byte aligned row-major matrix";
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return "cuTensorMapEncodeTiled entry point not available";
     // (columns, rows of one batch entry, batch entries): a block never spills into the next batch entry's rows
     const long batches = rows / p->g.W;
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(p->e.out32_stride), static_cast<cuuint64_t>(p->g.W), static_cast<cuuint64_t>(batches)};
-    cuuint64_t str[2] = {static_cast<cuuint64_t>(p->e.out32_stride) * 4, static_cast<cuuint64_t>(p->e.out32_stride) * 4 * p->g.W};
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(stride), static_cast<cuuint64_t>(p->g.W), static_cast<cuuint64_t>(batches)};
+    cuuint64_t str[2] = {static_cast<cuuint64_t>(stride) * esz, static_cast<cuuint64_t>(stride) * esz * p->g.W};
     cuuint32_t box[3] = {32, 32, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = fn(&p->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->e.out32, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(&p->tmO, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "tma store: cuTensorMapEncodeTiled failed";
     p->e.tma_store = 1;
     return nullptr;

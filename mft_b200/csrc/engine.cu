@@ -112,6 +112,8 @@ struct mftb200_ctx {
     std::vector<cudaEvent_t> prof_events;   // pairs
     std::vector<int> prof_kinds, prof_tags;
     int cur_slot = 0, cur_pairs = 0;       // cur_pairs / cur_b0: size and first pair of the sub-batch being enqueued
+    int corr_plan = -1, corr_bulk = 1;
+    bool corr_bulk_ok = false;
     float* out_cur = nullptr;              // where the upsampling kernel writes: the caller's buffer of the current refine
     // Deferred context encoder.  cnet(t) is only read when frame t is the LEFT image of a pair, i.e. from the next frame
     // on, so it does not have to sit on frame t's critical path: encode_frame runs fnet (+ cnet's first convolution, which
@@ -151,6 +153,8 @@ struct mftb200_ctx {
         enc_f_steps.clear(); ctx_first_steps.clear(); ctx_rest_steps.clear();
         pending_ctx_slot = -1;
         ctx_done_valid = false;
+        corr_plan = -1;
+        corr_bulk_ok = false;
         configured = false;
     }
 };
@@ -335,6 +339,10 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         if (i >= 0) {
             ConvEpi& e = B.epi(i);
             e.scale = 0.0625f; e.out16 = c->corr[0]; e.out16_stride = npx; e.out16_coff = 0; e.n_valid = npx;
+            // the volume can leave the CTA as bulk tensor stores (32 x 32 fp16 blocks) instead of per-thread stores
+            c->corr_plan = i;
+            c->corr_bulk_ok = conv_plan_enable_tma_store(&c->plans[i], static_cast<long>(mp) * npx) == nullptr;
+            c->plans[i].e.tma_store = (c->corr_bulk_ok && c->corr_bulk) ? 1 : 0;
         }
         c->pre_steps.push_back(B.step(i, true));
     }
@@ -1001,6 +1009,11 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     }
     if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "corr_bulk_store") == 0) {
+        c->corr_bulk = value ? 1 : 0;
+        if (c->corr_plan >= 0) c->plans[c->corr_plan].e.tma_store = (c->corr_bulk_ok && c->corr_bulk) ? 1 : 0;
+        return MFTB200_OK;
+    }
     if (strcmp(key, "defer_context") == 0) { c->defer_context = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }

@@ -142,6 +142,26 @@ def test_padded_size_vs_reference_golden(seeded_weights):
     assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
 
 
+@pytest.mark.parametrize('size', [(128, 160), (256, 256)])
+def test_corr_bulk_store_bit_identical(size, seeded_weights):
+    """The correlation volume written as bulk tensor stores (fp16 blocks, 64-byte swizzle) vs per-thread stores."""
+    from mft_b200.synth import synthetic_video
+    H, Wd = size
+    frames = list(synthetic_video(3, H, Wd, seed=11))
+    eng = _engine(seeded_weights, H, Wd, pairs=2)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    n = (H // 8) * (Wd // 8)
+    res = {}
+    for mode in (0, 1):
+        eng.set_option('corr_bulk_store', mode)
+        out = eng.refine([0, 1], [2, 2]).clone()
+        eng.check_device()
+        res[mode] = (out, eng.debug_buffer('corr_l0', torch.float16, (2, n, n)).clone())
+    assert torch.equal(res[0][1], res[1][1]) and float(res[0][1].float().abs().max()) > 0
+    assert torch.equal(res[0][0], res[1][0])
+
+
 def test_batched_equals_single_pair(seeded_weights):
     """A pair's result must not depend on what else is in the batch (bit-exact)."""
     from mft_b200.synth import synthetic_video
