@@ -439,12 +439,34 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
     const __half* src = L0 + row * h * w;
     // every level is the fp32 average of the level above as it is STORED (fp16), rounded once: what avg_pool2d of the
     // stored volume gives (core/corr.py:26-28)
-    for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
-        const int y = i / w1, x = i % w1;
-        const __half* q = src + (2 * y) * w + 2 * x;
-        const __half r = __float2half_rn((((__half2float(q[0]) + __half2float(q[1])) + __half2float(q[w])) + __half2float(q[w + 1])) * 0.25f);
-        s1[i] = __half2float(r);
-        L1[row * h1 * w1 + i] = r;
+    if ((w & 7) == 0) {
+        // 16-byte loads: one thread = 8 columns of the row pair (2y, 2y+1) -> 4 outputs, one 8-byte store
+        const int w8 = w >> 3;
+        for (int i = threadIdx.x; i < h1 * w8; i += blockDim.x) {
+            const int y = i / w8, g = i - y * w8;
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + (2 * y) * w) + g);
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + (2 * y + 1) * w) + g);
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            __half r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&av[j]));
+                const float2 u = __half22float2(*reinterpret_cast<const __half2*>(&bv[j]));
+                r[j] = __float2half_rn((((t.x + t.y) + u.x) + u.y) * 0.25f);
+                s1[y * w1 + 4 * g + j] = __half2float(r[j]);
+            }
+            const __half2 p01 = __halves2half2(r[0], r[1]), p23 = __halves2half2(r[2], r[3]);
+            *reinterpret_cast<uint2*>(L1 + row * h1 * w1 + y * w1 + 4 * g) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&p01), *reinterpret_cast<const uint32_t*>(&p23));
+        }
+    } else {
+        for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
+            const int y = i / w1, x = i % w1;
+            const __half* q = src + (2 * y) * w + 2 * x;
+            const __half r = __float2half_rn((((__half2float(q[0]) + __half2float(q[1])) + __half2float(q[w])) + __half2float(q[w + 1])) * 0.25f);
+            s1[i] = __half2float(r);
+            L1[row * h1 * w1 + i] = r;
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
