@@ -333,18 +333,19 @@ void launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums,
     launch_pdl(instnorm_stats_kernel, grid, dim3(kStatThreads), 0, stream, raw, P, C, pix_per_block, sums);
 }
 
+// 16-byte accesses: one thread = 8 consecutive channels of one pixel (C % 8 == 0: 64 / 96 / 128), two per thread
 __global__ void __launch_bounds__(256)
-instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict__ sums, int P, int C, int relu,
-                      const __half2* __restrict__ res, __half2* __restrict__ out, long total2) {
+instnorm_apply_kernel(const uint4* __restrict__ raw, const double* __restrict__ sums, int P, int C, int relu,
+                      const uint4* __restrict__ res, uint4* __restrict__ out, long total8) {
     pdl_enter();
     // per-channel mean / rstd once per block (double: sum-of-squares minus square-of-sum cancels in fp32)
-    __shared__ float s_mean[128], s_rstd[128];
-    const int c2 = C / 2;
-    const long per_img2 = static_cast<long>(P) * c2;
-    const long i0 = static_cast<long>(blockIdx.x) * (blockDim.x * 8);
-    // element counts < 2^31: 32-bit divisions.  A block never straddles two images (P*C/2 % 2048 == 0 is not required:
-    // stragglers recompute below)
-    const int b = static_cast<int>(static_cast<unsigned>(i0) / static_cast<unsigned>(per_img2));
+    __shared__ __align__(16) float s_mean[128];
+    __shared__ __align__(16) float s_rstd[128];
+    const int c8 = C / 8;
+    const long per_img8 = static_cast<long>(P) * c8;
+    const long i0 = static_cast<long>(blockIdx.x) * (blockDim.x * 2);
+    // element counts < 2^31: 32-bit divisions.  A block may straddle two images: stragglers recompute below
+    const int b = static_cast<int>(static_cast<unsigned>(i0) / static_cast<unsigned>(per_img8));
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double* s = sums + static_cast<long>(b) * 2 * C;
         const double inv = 1.0 / P;
@@ -355,37 +356,55 @@ instnorm_apply_kernel(const __half2* __restrict__ raw, const double* __restrict_
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 2; ++k) {
         const long i = i0 + static_cast<long>(k) * blockDim.x + threadIdx.x;
-        if (i >= total2) break;
-        const int cp = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(c2));
-        float m0 = s_mean[2 * cp], m1 = s_mean[2 * cp + 1], r0 = s_rstd[2 * cp], r1 = s_rstd[2 * cp + 1];
-        if (static_cast<int>(static_cast<unsigned>(i) / static_cast<unsigned>(per_img2)) != b) {                              // rare: element of the next image inside this block
-            const double* s = sums + (i / per_img2) * 2 * C;
+        if (i >= total8) break;
+        const int c0 = static_cast<int>(static_cast<unsigned>(i) % static_cast<unsigned>(c8)) * 8;
+        float m[8], r[8];
+        *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(s_mean + c0);
+        *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(s_mean + c0 + 4);
+        *reinterpret_cast<float4*>(r) = *reinterpret_cast<const float4*>(s_rstd + c0);
+        *reinterpret_cast<float4*>(r + 4) = *reinterpret_cast<const float4*>(s_rstd + c0 + 4);
+        if (i >= static_cast<long>(b + 1) * per_img8) {            // rare: a pixel of the next image inside this block
+            const double* s = sums + (i / per_img8) * 2 * C;
             const double inv = 1.0 / P;
-            const double a0 = s[2 * cp] * inv, a1 = s[2 * cp + 1] * inv;
-            m0 = static_cast<float>(a0); m1 = static_cast<float>(a1);
-            r0 = static_cast<float>(1.0 / sqrt(fmax(s[C + 2 * cp] * inv - a0 * a0, 0.0) + 1e-5));
-            r1 = static_cast<float>(1.0 / sqrt(fmax(s[C + 2 * cp + 1] * inv - a1 * a1, 0.0) + 1e-5));
+            for (int j = 0; j < 8; ++j) {
+                const double a0 = s[c0 + j] * inv;
+                m[j] = static_cast<float>(a0);
+                r[j] = static_cast<float>(1.0 / sqrt(fmax(s[C + c0 + j] * inv - a0 * a0, 0.0) + 1e-5));
+            }
         }
-        const float2 x = __half22float2(raw[i]);
-        float y0 = (x.x - m0) * r0, y1 = (x.y - m1) * r1;
-        if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+        const uint4 xv = raw[i];
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t rw[4] = {0u, 0u, 0u, 0u};
         if (res != nullptr) {
-            const float2 r = __half22float2(res[i]);
-            y0 = fmaxf(y0 + r.x, 0.f);
-            y1 = fmaxf(y1 + r.y, 0.f);
+            const uint4 rv = res[i];
+            rw[0] = rv.x; rw[1] = rv.y; rw[2] = rv.z; rw[3] = rv.w;
         }
-        out[i] = __floats2half2_rn(y0, y1);
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&xw[j]));
+            float y0 = (x.x - m[2 * j]) * r[2 * j], y1 = (x.y - m[2 * j + 1]) * r[2 * j + 1];
+            if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            if (res != nullptr) {
+                const float2 q = __half22float2(*reinterpret_cast<const __half2*>(&rw[j]));
+                y0 = fmaxf(y0 + q.x, 0.f);
+                y1 = fmaxf(y1 + q.y, 0.f);
+            }
+            const __half2 o = __floats2half2_rn(y0, y1);
+            ow[j] = *reinterpret_cast<const uint32_t*>(&o);
+        }
+        out[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
 }
 
 void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
                            __half* out, cudaStream_t stream) {
-    const long total2 = static_cast<long>(B) * P * C / 2;
-    launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total2 + 2047) / 2048)), dim3(256), 0, stream,
-               reinterpret_cast<const __half2*>(raw), sums, P, C, relu, reinterpret_cast<const __half2*>(res),
-               reinterpret_cast<__half2*>(out), total2);
+    const long total8 = static_cast<long>(B) * P * C / 8;
+    launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total8 + 511) / 512)), dim3(256), 0, stream,
+               reinterpret_cast<const uint4*>(raw), sums, P, C, relu, reinterpret_cast<const uint4*>(res),
+               reinterpret_cast<uint4*>(out), total8);
 }
 
 // ==========================================================================================

@@ -30,6 +30,8 @@ for r in range(reps):
     eng.profile_fetch()
     eng.set_option('profile', 0)
     seen_prog = False
+    if r == 0 and os.environ.get('STEP_DETAIL'):
+        print('per step (us, kind 0 = tensor-core launch, layer tag):', ' '.join(f'{ms * 1e3:.1f}/{kind}/{layer}' for ms, kind, layer in st))
     for ms, kind, layer in st:
         if layer == 200 or layer == 201:
             name, seen_prog = 'iteration program (conv_prog_kernel)', True
