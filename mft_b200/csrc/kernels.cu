@@ -256,30 +256,40 @@ void launch_warp_forward(const float* flow, const float* img, const uint8_t* mas
 __global__ void __launch_bounds__(256)
 frame_patches_kernel(const uint8_t* __restrict__ bgr, int H, int W, int Hp, int Wp, int pl, int pt,
                      __half* __restrict__ patches, long total8) {
+    // 2 * (u / 255) - 1 for the 256 byte values, once per block (the same fp32 expression, so the same bits as per entry);
+    // independent of the previous kernel: built before the dependency wait
+    __shared__ __half lut[256];
+    lut[threadIdx.x] = __float2half_rn(2.0f * (static_cast<float>(threadIdx.x) / 255.0f) - 1.0f);
     pdl_enter();
+    __syncthreads();
     const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total8) return;
-    const int seg = static_cast<int>(i % 19);
-    const long op = i / 19;
-    const int Wo = Wp / 2;
-    const int oy = static_cast<int>(op / Wo), ox = static_cast<int>(op - static_cast<long>(oy) * Wo);
-    __align__(16) __half v8[8];
+    const unsigned iu = static_cast<unsigned>(i);                    // total8 < 2^31: 32-bit divisions
+    const unsigned op = iu / 19u;
+    const int seg = static_cast<int>(iu - op * 19u);
+    const unsigned Wo = static_cast<unsigned>(Wp / 2);
+    const int oy = static_cast<int>(op / Wo), ox = static_cast<int>(op - static_cast<unsigned>(oy) * Wo);
+    const __half zero = __float2half_rn(0.0f);
+    __half v8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = seg * 8 + j;
-        float v = 0.0f;
+        __half v = zero;
         if (k < 147) {
-            const int tap = k / 3, c = k - tap * 3, ky = tap / 7, kx = tap - ky * 7;
+            const int tap = (k * 171) >> 9, c = k - tap * 3, ky = (tap * 37) >> 8, kx = tap - ky * 7;      // k / 3 (k < 256), tap / 7 (tap < 49)
             const int yp = 2 * oy + ky - 3, xp = 2 * ox + kx - 3;
             if (yp >= 0 && yp < Hp && xp >= 0 && xp < Wp) {
                 const int ys = min(max(yp - pt, 0), H - 1), xs = min(max(xp - pl, 0), W - 1);
-                const float u = static_cast<float>(__ldg(bgr + (static_cast<long>(ys) * W + xs) * 3 + (2 - c)));
-                v = 2.0f * (u / 255.0f) - 1.0f;
+                v = lut[__ldg(bgr + (ys * W + xs) * 3 + (2 - c))];
             }
         }
-        v8[j] = __float2half_rn(v);
+        v8[j] = v;
     }
-    *reinterpret_cast<uint4*>(patches + i * 8) = *reinterpret_cast<const uint4*>(v8);
+    const __half2 p0 = __halves2half2(v8[0], v8[1]), p1 = __halves2half2(v8[2], v8[3]), p2 = __halves2half2(v8[4], v8[5]),
+                  p3 = __halves2half2(v8[6], v8[7]);
+    *reinterpret_cast<uint4*>(patches + i * 8) =
+        make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                   *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
 }
 
 void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
