@@ -615,13 +615,39 @@ void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256)
 upsample_kernel(const UpsampleArgs a) {
     pdl_enter();
+    // The 64 threads of a coarse pixel blend the same 3x3 neighbours: 36 threads of the block fetch them once
+    // ([8 * flow x, 8 * flow y, occlusion logits 0 / 1, log-variance]; zeros outside the image = F.unfold's padding).
+    __shared__ float nb[4][9][5];
     const int npx = a.h * a.w;
-    const long pp = static_cast<long>(blockIdx.x) * 4 + (threadIdx.x >> 6);
-    if (pp >= static_cast<long>(a.n_pairs) * npx) return;
+    const long total = static_cast<long>(a.n_pairs) * npx;
+    if (threadIdx.x < 36) {
+        const int qd = threadIdx.x / 9, k = threadIdx.x - qd * 9;
+        const long pq = static_cast<long>(blockIdx.x) * 4 + qd;
+        float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (pq < total) {
+            const int pr = static_cast<int>(static_cast<unsigned>(pq) / static_cast<unsigned>(npx)), nq = static_cast<int>(pq) - pr * npx;
+            const int yq = nq / a.w, xq = nq - yq * a.w;
+            const int yy = yq + k / 3 - 1, xx = xq + k % 3 - 1;
+            if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) {
+                const long q = pq - nq + static_cast<long>(yy) * a.w + xx;
+                const float2 c = *reinterpret_cast<const float2*>(a.coords1 + q * 2);
+                const float4 ou = *reinterpret_cast<const float4*>(a.ou32 + q * 4);
+                v[0] = 8.0f * (c.x - static_cast<float>(xx));
+                v[1] = 8.0f * (c.y - static_cast<float>(yy));
+                v[2] = ou.x; v[3] = ou.y; v[4] = ou.z;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) nb[qd][k][j] = v[j];
+    }
+    __syncthreads();
+    const int qd = threadIdx.x >> 6;
+    const long pp = static_cast<long>(blockIdx.x) * 4 + qd;
+    if (pp >= total) return;
     const int sub = threadIdx.x & 63;
     const int sy = sub >> 3, sx = sub & 7;
     const int pair = static_cast<int>(static_cast<unsigned>(pp) / static_cast<unsigned>(npx)), n = static_cast<int>(pp) - pair * npx;
-    const int y = n / a.w, x = n % a.w;
+    const int y = n / a.w, x = n - y * a.w;
     const float* m = a.mask32 + pp * 576 + sub;
     float mk[9];
     float mx = -INFINITY;
@@ -633,24 +659,16 @@ upsample_kernel(const UpsampleArgs a) {
     float den = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-        mk[k] = expf(mk[k] - mx);
+        mk[k] = __expf(mk[k] - mx);          // ex2.approx: 2 ulp on weights that multiply fp16-operand results
         den += mk[k];
     }
+    const float inv_den = 1.0f / den;
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    const long pbase = pp - n;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
-        if (yy < 0 || yy >= a.h || xx < 0 || xx >= a.w) continue;
-        const long q = pbase + static_cast<long>(yy) * a.w + xx;
-        const float wk = mk[k] / den;
-        const float2 c = *reinterpret_cast<const float2*>(a.coords1 + q * 2);
-        const float4 ou = *reinterpret_cast<const float4*>(a.ou32 + q * 4);
-        acc[0] += wk * (8.0f * (c.x - static_cast<float>(xx)));
-        acc[1] += wk * (8.0f * (c.y - static_cast<float>(yy)));
-        acc[2] += wk * ou.x;
-        acc[3] += wk * ou.y;
-        acc[4] += wk * ou.z;
+        const float wk = mk[k] * inv_den;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[j] = fmaf(wk, nb[qd][k][j], acc[j]);
     }
     const int Y = 8 * y + sy - a.pad_top, Xo = 8 * x + sx - a.pad_left;
     if (Y < 0 || Y >= a.H || Xo < 0 || Xo >= a.W) return;
