@@ -59,6 +59,10 @@ int mftb200_configure(mftb200_ctx* ctx, int H, int W, int max_pairs, int n_slots
 /* fnet + cnet of one frame, once, into feature slot `slot`.  bgr: (H,W,3) uint8; on_device=0
  * means a host pointer (copied with cudaMemcpyAsync on `stream`; pin it for overlap). */
 int mftb200_encode_frame(mftb200_ctx* ctx, const uint8_t* bgr, int on_device, int slot, mftb200_stream stream);
+/* 1 if `p` points into page-locked (pinned / registered) host memory, i.e. the frame copy of encode_frame is a true
+ * asynchronous DMA and a binding need not stage the frame itself (the reference's `.cuda()` at MFT/raft.py:45 stages
+ * pageable frames inside the driver); 0 for pageable or device memory. */
+int mftb200_is_pinned_host(const void* p);
 
 /* ---- batched RAFT refinement (RAFT.forward part 2 + RAFTWrapper.compute_flow post-processing:
  * MFT/RAFT/core/raft.py:141-259, MFT/raft.py:56-62) ---------------------------------------- */

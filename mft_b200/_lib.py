@@ -28,6 +28,7 @@ def _declare(lib):
         'mftb200_upload_layer': (ci, [vp, ci, vp, vp, ci, ci, ci]),
         'mftb200_configure': (ci, [vp, ci, ci, ci, ci, ci]),
         'mftb200_encode_frame': (ci, [vp, vp, ci, ci, vp]),
+        'mftb200_is_pinned_host': (ci, [vp]),
         'mftb200_raft_refine': (ci, [vp, ci, C.POINTER(ci), C.POINTER(ci), vp, vp]),
         'mftb200_chain_select': (ci, [ci, C.POINTER(vp), vp, cf, ci, ci, vp, vp, vp]),
         'mftb200_warp_backward': (ci, [vp, vp, ci, ci, ci, ci, vp, vp]),

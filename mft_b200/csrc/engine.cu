@@ -845,6 +845,16 @@ int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int 
     return MFTB200_OK;
 }
 
+int mftb200_is_pinned_host(const void* p) {
+    if (!p) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();          // unregistered host memory reports an error on old drivers: not sticky
+        return 0;
+    }
+    return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, const int* right_slots, float* out,
                         mftb200_stream stream) {
     if (!c) return MFTB200_ERR_ARG;
@@ -1068,7 +1078,7 @@ int mftb200_profile_fetch(mftb200_ctx* c, double* ms_by_kind, long long* steps_b
 int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* bytes) {
     if (!c || !name || !ptr || !bytes) return MFTB200_ERR_ARG;
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "debug_buffer: not configured");
-    if (c->pending_ctx_slot >= 0 && c->last_main != nullptr) flush_context(c, c->last_main, c->last_main);
+    if (c->pending_ctx_slot >= 0) flush_context(c, c->last_main, c->last_main);      // (last_main may be stream 0, the default stream)
     const size_t npx = c->npx, M = npx * c->max_pairs;
     struct Ent { const char* n; void* p; size_t b; };
     const Ent tab[] = {

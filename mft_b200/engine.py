@@ -59,6 +59,11 @@ class Engine:
             return
         frame = np.asarray(frame)
         assert frame.dtype == np.uint8 and frame.shape == (H, W, 3), (frame.dtype, frame.shape)
+        if frame.flags.c_contiguous and self.L.mftb200_is_pinned_host(C.c_void_p(frame.ctypes.data)):
+            # the caller's frame is page-locked: DMA straight from it (the caller keeps it unchanged until the result of this
+            # frame is back, like the reference, whose memory holds references to the caller's frames, MFT.py:150)
+            _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(frame.ctypes.data), 0, slot, _stream_ptr()), self.ctx)
+            return
         # stage through pinned memory so the H2D copy is asynchronous w.r.t. the host
         torch.cuda.current_stream().synchronize()
         self._pinned.numpy()[...] = frame

@@ -162,6 +162,30 @@ def test_corr_bulk_store_bit_identical(size, seeded_weights):
     assert torch.equal(res[0][0], res[1][0])
 
 
+def test_pinned_frame_is_read_in_place(seeded_weights):
+    """A frame in page-locked host memory is DMA'd straight from the caller's buffer; same features as the staged path."""
+    from mft_b200 import _lib
+    from mft_b200.synth import synthetic_video
+    import ctypes
+    H, Wd = 128, 160
+    f = list(synthetic_video(1, H, Wd, seed=21))[0]
+    pin = torch.from_numpy(f).pin_memory()
+    L = _lib.lib()
+    a, b = L.mftb200_is_pinned_host(ctypes.c_void_p(pin.data_ptr())), L.mftb200_is_pinned_host(ctypes.c_void_p(f.ctypes.data))
+    assert (a, b) == (1, 0), (a, b)
+    eng = _engine(seeded_weights, H, Wd)
+    eng.encode_frame(f, 0)
+    eng.encode_frame(pin.numpy(), 1)
+    n = (H // 8) * (Wd // 8)
+    fm = eng.debug_buffer('fmap_slots', torch.float16, (2, n, 256)).float()
+    net = eng.debug_buffer('net_slots', torch.float32, (2, n, 128))
+    eng.check_device()
+    # (instance-norm statistics are accumulated with atomics: two encodes of one frame agree to fp16 round-off, not bit for bit)
+    dfm, dnet = float((fm[0] - fm[1]).abs().max()), float((net[0] - net[1]).abs().max())
+    assert float(fm.abs().max()) > 0 and dfm <= 4e-3 * float(fm.abs().max()), (dfm, float(fm.abs().max()))
+    assert dnet <= 1e-5 * max(1.0, float(net.abs().max())), dnet
+
+
 def test_batched_equals_single_pair(seeded_weights):
     """A pair's result must not depend on what else is in the batch (bit-exact)."""
     from mft_b200.synth import synthetic_video
