@@ -214,8 +214,29 @@ def _gloo_worker(rank, world, port, out):
     import torch.distributed as dist
     from mft_b200.dist import FlowShardedTracker
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
-    out.put((rank, _run_sharded(world)))
+    out.put((rank, (_run_sharded(world), _run_delta_sharded(world))))
     dist.destroy_process_group()
+
+
+def _run_delta_sharded(world):
+    """Per-delta sharding inside a frame: stand-in flow / select functions that depend on the chain
+    identity and on the ORDER of the gathered fields, so a wrong owner, slot or order changes the sums."""
+    from mft_b200.dist import DeltaShardedTracker
+    H, W, T = 5, 7, 40
+    deltas = [np.inf, 1, 2, 4, 8, 16, 32]
+    calls = []
+
+    def flow_fn(t, live):
+        calls.append(len(live))
+        return torch.stack([torch.full((4, H, W), float(t * 100 + (0 if np.isinf(d) else d)) + 0.25 * left) for d, left in live])
+
+    def select_fn(lefts, right):
+        w = torch.arange(1, len(lefts) + 1, dtype=torch.float32).view(-1, 1, 1, 1)
+        return (torch.stack(lefts) * 0.125 + right * w).sum(0) / float(len(lefts)) % 977.0
+    trk = DeltaShardedTracker(deltas, (H, W), flow_fn, select_fn, 'cpu')
+    sums = [float(trk.track().sum()) for _ in range(T)]
+    assert max(calls) <= (7 + world - 1) // world              # no rank refines more than ceil(K / G) pairs per frame
+    return sums
 
 
 def _run_sharded(world):
@@ -235,7 +256,7 @@ def _run_sharded(world):
 
 def test_flow_sharding_world2_gloo_matches_single_process():
     import torch.multiprocessing as mp
-    want = _run_sharded(1)
+    want = (_run_sharded(1), _run_delta_sharded(1))
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
