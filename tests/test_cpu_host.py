@@ -357,3 +357,26 @@ def test_point_queries_cpu_paths_match_reference_golden():
     assert np.abs(res.chain(torch.from_numpy(g['other'])).numpy() - g['chained']).max() < 1e-4
     assert np.abs(res.warp_backward(torch.from_numpy(g['img'])).numpy() - g['warped_img']).max() < 1e-5
     assert np.array_equal(res.invalid_mask().numpy(), g['invalid'])
+
+
+def test_roofline_flop_counts_follow_the_layer_shapes():
+    """bench.py's algorithmic FLOPs (roofline numerators) recomputed from the checkpoint's layer shapes."""
+    import bench
+    spec = {n[:-7]: s for n, s in O.weight_spec() if n.endswith('.weight') and len(s) == 4}
+    f = lambda name: 2 * int(np.prod(spec[name]))                         # 2 * cout * cin * kh * kw per output pixel
+    ub = 'update_block.'
+    per_iter = sum(f(ub + n) for n in ('encoder.convc1', 'encoder.convc2', 'encoder.convf1', 'encoder.convf2', 'encoder.conv',
+                                       'gru.convz1', 'gru.convr1', 'gru.convq1', 'gru.convz2', 'gru.convr2', 'gru.convq2',
+                                       'flow_head.conv1', 'flow_head.conv2'))
+    assert per_iter == 5351936                                             # one conv_prog_kernel launch, per coarse pixel
+    last = per_iter + f(ub + 'mask.0') + f(ub + 'mask.2')
+    ou = sum(f('occlusion_block.' + n) for n in ('occl_head.conv1', 'occl_head.conv2', 'uncertainty_head.conv1', 'uncertainty_head.conv2'))
+    assert (last, ou) == (6236672, 3287808)
+    enc2 = f('fnet.conv1') + sum(f(f'fnet.layer1.{b}.conv{c}') for b in (0, 1) for c in (1, 2))
+    assert enc2 == 18816 + 4 * 73728
+    H = W = 512
+    n = (H // 8) * (W // 8)
+    F = bench.flops_per_frame(H, W)
+    assert abs(F - 2.09e12) < 0.01e12
+    assert F == 2 * ((H // 2) * (W // 2) * enc2 + (H // 4) * (W // 4) * 620544 + n * (1130496 + 65536)) + \
+        7 * (2 * n * n * 256 + 11 * n * per_iter + n * last + n * ou)
