@@ -1015,41 +1015,52 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int rx = g.kw / 2, ry = g.kh / 2;
     bool ok = true;
 
+    // warp-uniform role loops, asynchronous instructions issued by one elected lane (see conv_tc_kernel)
     if (warp == 0) {
-        if (lane == 0) {
-            const int x0 = tx * 16 - rx, y0 = ty * 16 - ry;
-            const int brow = ny * g.n_tile;
-            int it = 0;
-            for (int kc = 0; kc < g.kchunks && ok; ++kc) {
-                const int sa = kc % g.na;
-                if (!mbar_wait(&a_empty[sa], ((kc / g.na) & 1) ^ 1)) { ok = false; break; }
+        // A producer: one haloed activation box per 64-channel chunk
+        const int x0 = tx * 16 - rx, y0 = ty * 16 - ry;
+        int sa = 0;
+        uint32_t pa = 0;
+        for (int kc = 0; kc < g.kchunks; ++kc) {
+            if (!__all_sync(0xffffffffu, mbar_wait(&a_empty[sa], pa ^ 1))) { ok = false; break; }
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&a_full[sa], a_bytes);
                 tma_load_4d(smem + static_cast<size_t>(sa) * a_bytes, &tmA, &a_full[sa], kc * kChunkK, x0, y0, b);
-                for (int tap = 0; tap < g.ntaps; ++tap, ++it) {
-                    const int sb = it % g.nb;
-                    if (!mbar_wait(&b_empty[sb], ((it / g.nb) & 1) ^ 1)) { ok = false; break; }
+            }
+            __syncwarp();
+            if (++sa == g.na) { sa = 0; pa ^= 1; }
+        }
+    } else if (warp == 2) {
+        // B producer: one weight slab per (chunk, tap), shared by both 128-row halves
+        const int brow = ny * g.n_tile;
+        int sb = 0;
+        uint32_t pb = 0;
+        for (int kc = 0; kc < g.kchunks && ok; ++kc) {
+            for (int tap = 0; tap < g.ntaps; ++tap) {
+                if (!__all_sync(0xffffffffu, mbar_wait(&b_empty[sb], pb ^ 1))) { ok = false; break; }
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&b_full[sb], b_bytes);
-                    tma_load_2d(smem_b + static_cast<size_t>(sb) * b_bytes, &tmB, &b_full[sb],
-                                (tap * g.kchunks + kc) * kChunkK, brow);
+                    tma_load_2d(smem_b + static_cast<size_t>(sb) * b_bytes, &tmB, &b_full[sb], (tap * g.kchunks + kc) * kChunkK, brow);
                 }
+                __syncwarp();
+                if (++sb == g.nb) { sb = 0; pb ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
-            const uint32_t sbo = static_cast<uint32_t>(g.pxp) * 128;
-            int it = 0;
-            for (int kc = 0; kc < g.kchunks && ok; ++kc) {
-                const int sa = kc % g.na;
-                if (!mbar_wait(&a_full[sa], (kc / g.na) & 1)) { ok = false; break; }
-                const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(sa) * a_bytes);
-                int kx = 0, ky = 0;
-                for (int tap = 0; tap < g.ntaps; ++tap, ++it) {
-                    const int sb = it % g.nb;
-                    if (!mbar_wait(&b_full[sb], (it / g.nb) & 1)) { ok = false; break; }
-                    if (tstamp && it == 0) tstamp[2] = clock64();
-                    tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(kTileM, g.n_tile);
+        const uint32_t sbo = static_cast<uint32_t>(g.pxp) * 128;
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        bool first = true;
+        for (int kc = 0; kc < g.kchunks && ok; ++kc) {
+            if (!__all_sync(0xffffffffu, mbar_wait(&a_full[sa], pa))) { ok = false; break; }
+            const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(sa) * a_bytes);
+            int kx = 0, ky = 0;
+            for (int tap = 0; tap < g.ntaps; ++tap) {
+                if (!__all_sync(0xffffffffu, mbar_wait(&b_full[sb], pb))) { ok = false; break; }
+                tc_fence_after();
+                if (elect_one()) {
+                    if (tstamp && first) tstamp[2] = clock64();
                     const uint32_t b_addr = smem_u32(smem_b + static_cast<size_t>(sb) * b_bytes);
                     const uint32_t a_tap = a_addr + static_cast<uint32_t>(ky * g.pxp + kx) * 128;
 #pragma unroll
@@ -1058,13 +1069,21 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int k = 0; k < 4; ++k)
                             umma_f16(tmem_base + half * g.n_tile,
                                      umma_desc_k128_ex(a_tap + half * 8 * 128 + k * 32, sbo, g.base_off_mode),
-                                     umma_desc_k128(b_addr + k * 32), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                                     umma_desc_k128(b_addr + k * 32), idesc, (!first || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&b_empty[sb]);
-                    if (++kx == g.kw) { kx = 0; ++ky; }
                 }
-                umma_commit(&a_empty[sa]);
+                __syncwarp();
+                first = false;
+                if (++kx == g.kw) { kx = 0; ++ky; }
+                if (++sb == g.nb) { sb = 0; pb ^= 1; }
             }
+            if (!ok) break;
+            if (elect_one()) umma_commit(&a_empty[sa]);
+            __syncwarp();
+            if (++sa == g.na) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one()) {
             if (tstamp) tstamp[3] = clock64();
             umma_commit(accum_ready);
         }
