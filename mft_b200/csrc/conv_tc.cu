@@ -1238,11 +1238,12 @@ void choose_tile(int H, int W, int* tile_h, int* tile_w) {
     }
 }
 
-// Variant 2 is correct but was not faster when it was measured -- BEFORE the warp-uniform issue fix (its TMA / MMA loops
-// still issue from a divergent `lane == 0` branch, ~67 cycles per MMA): off by default, kept under test.  With uniform
-// issue the variant-1 main loop is bound by the ~70-95 B/clk an SM ingests from L2, which is exactly what the haloed
-// tile and the shared weight slab cut (3.8x less ingress for the 64-channel encoder layers), so it is worth
-// re-measuring with elect.sync issue and an epilogue that accumulates the instance-norm statistics.
+// Variant 2 is correct but was not faster when it was measured -- BEFORE the warp-uniform issue fix, when its TMA / MMA
+// loops still issued from a divergent `lane == 0` branch (~67 cycles per MMA): off by default, kept under test.  Its
+// role loops are warp-uniform now (parity tests green) but it has NOT been re-timed yet.  With uniform issue the
+// variant-1 main loop is bound by the ~70-95 B/clk an SM ingests from L2, which is exactly what the haloed tile and the
+// shared weight slab cut (3.8x less ingress for the 64-channel encoder layers); to serve fnet it still needs an epilogue
+// that accumulates the instance-norm statistics.
 // Measured: the UMMA swizzle is address based, so the base-offset field must stay 0.
 static int g_use_v2 = 0, g_v2_base_off = 0;
 void conv_set_v2(int on, int base_off_mode) { g_use_v2 = on; g_v2_base_off = base_off_mode; }
