@@ -236,6 +236,7 @@ def _run_delta_sharded(world):
     trk = DeltaShardedTracker(deltas, (H, W), flow_fn, select_fn, 'cpu')
     sums = [float(trk.track().sum()) for _ in range(T)]
     assert max(calls) <= (7 + world - 1) // world              # no rank refines more than ceil(K / G) pairs per frame
+    assert 0 in trk.results and len(trk.results) <= 33 and min(k for k in trk.results if k) == T - 31      # template + last 32
     return sums
 
 
