@@ -64,6 +64,14 @@ int mftb200_encode_frame(mftb200_ctx* ctx, const uint8_t* bgr, int on_device, in
  * pageable frames inside the driver); 0 for pageable or device memory. */
 int mftb200_is_pinned_host(const void* p);
 
+/* The feature-slot arrays themselves, for multi-GPU feature exchange (rank t % G encodes frame t, one
+ * all-gather hands every rank the features): fmap = fp16 [n_slots][h*w][256], net = fp32 [n_slots][h*w][128] (tanh half
+ * of cnet), inp = fp16 [n_slots][h*w][128] (relu half), h x w = padded H/8 x W/8; slot_bytes[3] = bytes of one slot in
+ * each array.  Work enqueued on `stream` after this call sees every encode_frame issued before it complete (incl. the
+ * context encoder that trails on the engine's own stream).  The reference has no counterpart (it re-runs the encoders
+ * per pair, MFT/RAFT/core/raft.py:130-149). */
+int mftb200_slot_buffers(mftb200_ctx* ctx, void** fmap, void** net, void** inp, size_t* slot_bytes, mftb200_stream stream);
+
 /* ---- batched RAFT refinement (RAFT.forward part 2 + RAFTWrapper.compute_flow post-processing:
  * MFT/RAFT/core/raft.py:141-259, MFT/raft.py:56-62) ---------------------------------------- */
 /* For each pair p: flow left_slots[p] -> right_slots[p].  out: device float (n_pairs,4,H,W). */
@@ -98,19 +106,25 @@ int mftb200_sample_points(const float* field, int C, int H, int W, const float* 
 int mftb200_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
                          float border, float* out, float* counts, mftb200_stream stream);
 
-/* ---- diagnostics / test hooks ---------------------------------------------------------------- */
-int mftb200_device_error_flag(mftb200_ctx* ctx);          /* syncs; 0 = clean */
-/* keys: "conv_impl" 0 = tcgen05 (product), 1 = SIMT cross-check kernel (tests only); "iters" = GRU
- * iterations; "profile" 0|1 = per-launch event timing (see mftb200_profile_fetch); "cluster" (0 = auto,
- * 1|2|4|8) and "smem_cap_kib" = conv-kernel tuning knobs read by the next mftb200_configure. */
+/* ---- error state / diagnostics --------------------------------------------------------------------- */
+/* Every pipeline wait inside the kernels is time bounded (2 s); a kernel that gives up raises a device flag instead of
+ * hanging the GPU.  The reference has no counterpart (its kernels are ATen's): the flag surfaces as the exception a
+ * CUDA error would raise under PyTorch (SURVEY 8b "Errors").
+ *   mftb200_device_error_flag   synchronises the device and reads the flag: 0 = clean.
+ *   mftb200_error_flag_async    enqueues a copy of the flag into a pinned mirror on `stream` (no synchronisation): call it
+ *                               behind a frame's work, next to the result's device->host copy;
+ *   mftb200_error_flag_poll     reads the mirror (valid once `stream` has been synchronised past the copy): 0 = clean.
+ * After a non-zero flag the context refuses encode_frame / raft_refine (MFTB200_ERR_DEVICE_FLAG) until
+ * mftb200_configure is called again: an aborted launch leaves the work queues of the persistent kernels undefined. */
+int mftb200_device_error_flag(mftb200_ctx* ctx);
+int mftb200_error_flag_async(mftb200_ctx* ctx, mftb200_stream stream);
+int mftb200_error_flag_poll(mftb200_ctx* ctx);
+/* Blocks the host until the newest encode_frame's host->device frame copy has left the caller's buffer (which may then
+ * be refilled; the reference copies synchronously at MFT/raft.py:45). */
+int mftb200_wait_frame_copied(mftb200_ctx* ctx);
+/* Product options: "iters" = GRU iterations (flow_config.flow_iters); "defer_context" 0|1; "profile" 0|1 = per-launch
+ * event timing (see mftb200_profile_fetch).  Test / tuning keys are listed in mft_b200/csrc/mft_b200_internal.h. */
 int mftb200_set_option(mftb200_ctx* ctx, const char* key, int value);
-/* Process-wide conv-kernel tuning knobs (read when plans are built): "conv_v2" bit0 = use the 256-pixel haloed
- * kernel, bit1 = descriptor base-offset mode; "pdl"; "cluster"; "smem_cap_kib". */
-int mftb200_set_global_option(const char* key, int value);
-/* Named internal buffer for stage-level parity tests ("fmap_slots", "net_slots", "corr_l0", ...). */
-int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t* bytes);
-/* Copies the first `bytes` bytes of a named internal buffer into caller device memory (syncs). */
-int mftb200_debug_read(mftb200_ctx* ctx, const char* name, void* dst_device, size_t bytes);
 /* Number of kernels launched by this context since creation (bench's gpu_launches). */
 long long mftb200_launch_count(const mftb200_ctx* ctx);
 
@@ -120,28 +134,6 @@ long long mftb200_launch_count(const mftb200_ctx* ctx);
 int mftb200_profile_fetch(mftb200_ctx* ctx, double* ms_by_kind /*[2]*/, long long* steps_by_kind /*[2]*/);
 /* Per-step event times in launch order (does not clear; call before mftb200_profile_fetch). */
 int mftb200_profile_steps(mftb200_ctx* ctx, float* ms, int* kinds, int max_steps, int* n_steps);
-
-/* Stand-alone convolution through the product kernel, for unit tests: x fp16 NHWC
- * (B,H,W,pitch) view of `cin` channels, packed weights as in upload_layer, taps = kh x kw
- * centred window, stride 1|2, output fp32 NHWC (B,Ho,Wo,cout_pad) = (acc + bias) [relu]. */
-int mftb200_conv2d_test(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
-                        const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
-                        float* out_dev, int impl, mftb200_stream stream);
-
-/* Same launch repeated `reps` times with device timing (tuning aid): cluster / smem_cap_kib < 0 keep the
- * current setting, 0 = automatic; avg_ms receives the mean of launches 2..reps. */
-int mftb200_conv2d_bench(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
-                         const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
-                         float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
-                         mftb200_stream stream);
-
-/* As above; timing_dev (device int64 [n_ctas][16], may be NULL) receives per-CTA phase timestamps of the LAST
- * launch: clock64 at entry, set-up done, first stage landed, MMAs issued, accumulator ready, epilogue done,
- * exit; [7] = globaltimer ns at entry. */
-int mftb200_conv2d_bench2(const uint16_t* x_dev, int B, int H, int W, int pitch, int cin, const uint16_t* w_dev,
-                          const float* bias_dev, int cout_pad, int n_tile, int kh, int kw, int stride, int relu,
-                          float* out_dev, int impl, int cluster, int smem_cap_kib, int reps, float* avg_ms,
-                          long long* timing_dev, mftb200_stream stream);
 
 #ifdef __cplusplus
 }

@@ -60,13 +60,15 @@ class MFT:
         finite = [d for d in self.C.deltas if np.isfinite(d)]
         if finite and max(finite) + 2 > TRACKER_SLOTS:
             raise ValueError(f'deltas up to {TRACKER_SLOTS - 2} are supported (feature-slot budget)')
-        self.engine = self.flower.ensure_geometry(self.img_H, self.img_W)
+        self.engine = self.flower.ensure_geometry(self.img_H, self.img_W, claim=True)
+        self._frame_in_place = False
         self._free_slots = list(range(TRACKER_SLOTS))
         if getattr(self, '_pool_shape', None) != (self.img_H, self.img_W):
             self._pool = _PinnedPool((4, self.img_H, self.img_W))
             self._pool_shape = (self.img_H, self.img_W)
         slot = self._free_slots.pop()
-        self.engine.encode_frame(img, slot)
+        if self.engine.encode_frame(img, slot):
+            self.engine.wait_frame_copied()
         self.memory = {start_frame_i: {'img': img, 'slot': slot,
                                        'result': FlowOUTrackingResult.identity((self.img_H, self.img_W), device=self.device)}}
         self.template_img = img.copy()
@@ -97,15 +99,18 @@ class MFT:
     def track(self, input_img, debug=False, **kwargs):
         """input_img: (H,W,3) uint8 BGR (numpy, or a CUDA uint8 tensor already resident in HBM).
         meta.result: template -> current field, on CPU (kwarg device_result=True leaves it on the GPU
-        and skips the device->host copy)."""
+        and skips the device->host copy).  A frame in page-locked host memory is DMA'd in place; it may be
+        refilled as soon as track() returns (like the reference, which copies at MFT/raft.py:45).
+        Raises MftB200Error if a kernel of this or (device_result=True: of an earlier) frame aborted."""
         meta = SimpleNamespace()
+        self.engine.error_flag_poll()                  # no sync: the mirror as of the last completed frame
         self.current_frame_i += self.time_direction
         right_id = self.current_frame_i
         H, W = self.img_H, self.img_W
         eng = self.engine
 
         slot = self._free_slots.pop()
-        eng.encode_frame(input_img, slot)
+        in_place = eng.encode_frame(input_img, slot)
         live = self.live_chains()
         K = len(live)
         right = torch.empty((K, 4, H, W), dtype=torch.float32, device=self.device)
@@ -143,15 +148,21 @@ class MFT:
         lefts = [self.memory[left_id]['result'].packed() for _, left_id in live]
         packed, index = chain_select(lefts, right, float(self.C.occlusion_threshold), want_index=bool(debug))
         result = FlowOUTrackingResult.from_packed(packed)
+        eng.error_flag_async()                         # rides behind this frame's work, next to the result copy
 
         if kwargs.get('device_result', False):
-            meta.result = result
+            # the caller's own object AND storage, like the reference's clone (MFT.py:145): `.cpu()` or in-place edits
+            # of meta.result must not reach the field stored in self.memory
+            meta.result = result.clone()
+            if in_place:
+                eng.wait_frame_copied()                # the caller may refill its pinned frame buffer after this call
         else:
             host = self._pool.take()                  # pinned slot: asynchronous D2H, one stream sync, no extra copy
             if host is None:
                 host = torch.empty((4, H, W), dtype=torch.float32)
             host.copy_(packed, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            eng.error_flag_poll()                      # this frame's flag: raises instead of returning garbage
             meta.result = FlowOUTrackingResult.from_packed(host)
         if debug:
             meta.selected_delta_i = index

@@ -1,4 +1,5 @@
-"""ctypes binding of libmft_b200.so (C ABI declared in include/mft_b200.h).
+"""ctypes binding of libmft_b200.so (C ABI declared in include/mft_b200.h; test / tuning hooks in
+mft_b200/csrc/mft_b200_internal.h).
 
 The product path has no CPU fallback: if the shared library is missing or fails to load, every
 entry point raises.  Loading the library does not need a GPU (symbol checks run on CPU)."""
@@ -29,12 +30,16 @@ def _declare(lib):
         'mftb200_configure': (ci, [vp, ci, ci, ci, ci, ci]),
         'mftb200_encode_frame': (ci, [vp, vp, ci, ci, vp]),
         'mftb200_is_pinned_host': (ci, [vp]),
+        'mftb200_slot_buffers': (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), vp]),
         'mftb200_raft_refine': (ci, [vp, ci, C.POINTER(ci), C.POINTER(ci), vp, vp]),
         'mftb200_chain_select': (ci, [ci, C.POINTER(vp), vp, cf, ci, ci, vp, vp, vp]),
         'mftb200_warp_backward': (ci, [vp, vp, ci, ci, ci, ci, vp, vp]),
         'mftb200_sample_points': (ci, [vp, ci, ci, ci, vp, ci, ci, vp, vp]),
         'mftb200_warp_forward': (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, vp]),
         'mftb200_device_error_flag': (ci, [vp]),
+        'mftb200_error_flag_async': (ci, [vp, vp]),
+        'mftb200_error_flag_poll': (ci, [vp]),
+        'mftb200_wait_frame_copied': (ci, [vp]),
         'mftb200_set_option': (ci, [vp, C.c_char_p, ci]),
         'mftb200_set_global_option': (ci, [C.c_char_p, ci]),
         'mftb200_debug_buffer': (ci, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]),

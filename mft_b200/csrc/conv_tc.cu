@@ -679,7 +679,8 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                 push(static_cast<uint32_t>(l * per_layer + r));
         }
         const uint32_t depth = static_cast<uint32_t>(P.tickets);
-        uint32_t n_issue = 0, n_done = 0, my_item = 0, idx = 0, spins = 0;
+        uint32_t n_issue = 0, n_done = 0, my_item = 0, idx = 0, spins = 0, give_up = 0;
+        unsigned long long t_idle = 0;
         bool have_idx = false, end_posted = false;
         for (;;) {
             bool progress = false;
@@ -776,9 +777,12 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
             if (progress) {
                 spins = 0;
             } else {
-                if (++spins > (1u << 21)) {
+                // time-based bound (see mbar_wait): after 2 s without progress raise the abort flag, give the role warps
+                // a few more rounds to see it, then leave
+                if (++spins == 1024u) t_idle = global_timer_ns();
+                if (spins > 1024u && (spins & 255u) == 0u && global_timer_ns() - t_idle > kWaitTimeoutNs) {
                     ctl->abort = 70;
-                    if (spins > (1u << 21) + 64u) break;
+                    if (++give_up > 64u) break;
                 }
                 __nanosleep(20);
             }

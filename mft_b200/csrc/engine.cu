@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/mft_b200.h"
+#include "mft_b200_internal.h"
 #include "conv.h"
 #include "kernels.h"
 
@@ -42,6 +43,8 @@ struct Act {           // NHWC fp16 view
 
 thread_local std::string g_create_error;
 
+inline const char* cu_err(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
+
 }  // namespace
 
 struct mftb200_ctx {
@@ -53,6 +56,9 @@ struct mftb200_ctx {
     int conv_impl = 0;
     long long launches = 0;
     int* err_flag = nullptr;
+    int* err_host = nullptr;               // pinned mirror of err_flag, refreshed by mftb200_error_flag_async
+    bool poisoned = false;                 // a kernel aborted: queue counters / arrival sets are undefined until reconfigured
+    cudaEvent_t ev_frame_copied = nullptr; // the newest frame's host->device copy has left the caller's buffer
     std::vector<void*> allocs;
 
     // encoder workspace
@@ -243,9 +249,8 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb2
         const int st = site++;
         B.epi(static_cast<int>(c->plans.size()) - 1).stats = c->sums + st * 256;
         S.push_back([=](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-            launch_instnorm_apply(raw, cc->sums + st * 256, 1, P, C, relu, res, out, s);
             cc->launches += 1;
-            return nullptr;
+            return cu_err(launch_instnorm_apply(raw, cc->sums + st * 256, 1, P, C, relu, res, out, s));
         });
     };
 
@@ -329,9 +334,8 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;        // first pixel row of this sub-batch
         PairSetup a{cc->slot_table + 2 * cc->cur_b0, cc->fmap_slots, cc->net_slots, cc->inp_slots, cc->F1 + o * 256,
                     cc->F2 + o * 256, cc->h32 + o * 128, cc->X + o * 512, cc->coords1 + o * 2, cc->cur_pairs, cc->h, cc->w};
-        launch_pair_setup(a, s);
         cc->launches++;
-        return nullptr;
+        return cu_err(launch_pair_setup(a, s));
     });
     {   // all-pairs correlation: D[n1, n2] = <F1[n1,:], F2[n2,:]> / sqrt(256)   (core/corr.py:53-69)
         Act in{c->F1, 256, 256, 1, npx};
@@ -350,10 +354,9 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
         const size_t n0 = static_cast<size_t>(cc->h) * cc->w, n1 = static_cast<size_t>(cc->h / 2) * (cc->w / 2),
                      n2 = static_cast<size_t>(cc->h / 4) * (cc->w / 4), n3 = static_cast<size_t>(cc->h / 8) * (cc->w / 8);
-        launch_corr_pool(cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3,
-                         static_cast<long>(cc->cur_pairs) * cc->npx, cc->h, cc->w, s);
         cc->launches++;
-        return nullptr;
+        return cu_err(launch_corr_pool(cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3,
+                                       static_cast<long>(cc->cur_pairs) * cc->npx, cc->h, cc->w, s));
     });
 
     // ---- one GRU iteration (core/raft.py:173-184, core/update.py:229-238) ------------------
@@ -369,9 +372,8 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         LookupArgs a{{cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3},
                      cc->coords1 + o * 2, cc->corr16 + o * 328, cc->flowpatch + o * 104, cc->X + o * 512, cc->cur_pairs,
                      cc->h, cc->w};
-        launch_lookup(a, s);
         cc->launches++;
-        return nullptr;
+        return cu_err(launch_lookup(a, s));
     });
     Act a_corr{c->corr16, 328, 324, h, w};
     Act a_c1{c->c1buf, 256, 256, h, w};
@@ -473,9 +475,8 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
         OuPackArgs a{cc->X + o * 512, cc->corr16 + o * 328, cc->coords1 + o * 2, cc->delta32 + o * 2, cc->oupack + o * 720,
                      cc->cur_pairs, cc->h, cc->w};
-        launch_ou_pack(a, s);
         cc->launches++;
-        return nullptr;
+        return cu_err(launch_ou_pack(a, s));
     });
     Fz.back().lane = 1;
     {
@@ -506,9 +507,8 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         UpsampleArgs a{cc->mask32 + o * 576, cc->coords1 + o * 2, cc->ou32 + o * 4,
                        cc->out_cur + static_cast<size_t>(cc->cur_b0) * 4 * cc->H * cc->W, cc->cur_pairs, cc->h, cc->w, cc->H, cc->W,
                        cc->pad_l, cc->pad_t};
-        launch_upsample(a, s);
         cc->launches++;
-        return nullptr;
+        return cu_err(launch_upsample(a, s));
     });
     c->fz_upsample = static_cast<int>(Fz.size()) - 1;
     // the four head convolutions as ONE persistent launch: mask1 -> mask2 (three 192-channel slices) || ou1 -> ou2
@@ -649,6 +649,14 @@ int mftb200_create(mftb200_ctx** out) {
         return MFTB200_ERR_CUDA;
     }
     cudaMemset(c->err_flag, 0, 256);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), 64, cudaHostAllocDefault) != cudaSuccess) {
+        g_create_error = "cudaHostAlloc failed";
+        cudaFree(c->err_flag);
+        delete c;
+        return MFTB200_ERR_CUDA;
+    }
+    memset(c->err_host, 0, 64);
+    cudaEventCreateWithFlags(&c->ev_frame_copied, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->gs[0][1], cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->gs[1][0], cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->gs[1][1], cudaStreamNonBlocking);
@@ -676,6 +684,8 @@ void mftb200_destroy(mftb200_ctx* c) {
         cudaFree(L.bias);
     }
     cudaFree(c->err_flag);
+    cudaFreeHost(c->err_host);
+    if (c->ev_frame_copied) cudaEventDestroy(c->ev_frame_copied);
     if (c->gs[0][1]) cudaStreamDestroy(c->gs[0][1]);
     if (c->gs[1][0]) cudaStreamDestroy(c->gs[1][0]);
     if (c->gs[1][1]) cudaStreamDestroy(c->gs[1][1]);
@@ -721,6 +731,12 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     for (int i = 0; i < L_COUNT; ++i)
         if (!c->layers[i].w) return c->fail(MFTB200_ERR_STATE, "configure: layer %d not uploaded", i);
     c->free_workspace();
+    if (c->poisoned) {                     // an aborted launch: start from a clean flag; the workspace (queues, counters) is rebuilt below
+        cudaDeviceSynchronize();
+        cudaMemset(c->err_flag, 0, 256);
+        c->err_host[0] = 0;
+        c->poisoned = false;
+    }
     c->H = H; c->W = W;
     const int ph = (8 - H % 8) % 8, pw = (8 - W % 8) % 8;
     c->pad_t = ph / 2; c->pad_l = pw / 2;
@@ -771,10 +787,9 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     Builder B{c};
     c->plans.reserve(128);
     c->enc_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
-        cudaMemsetAsync(cc->sums, 0, sizeof(double) * 16 * 2 * 128, s);
-        launch_frame_patches(cc->frame_u8, cc->H, cc->W, cc->Hp, cc->Wp, cc->pad_l, cc->pad_t, cc->patches, s);
+        if (const char* e = cu_err(cudaMemsetAsync(cc->sums, 0, sizeof(double) * 16 * 2 * 128, s))) return e;
         cc->launches++;
-        return nullptr;
+        return cu_err(launch_frame_patches(cc->frame_u8, cc->H, cc->W, cc->Hp, cc->Wp, cc->pad_l, cc->pad_t, cc->patches, s));
     });
     // fnet (caller's stream) and cnet (side stream) only share the read-only patch matrix: run them concurrently
     std::vector<mftb200_ctx::Step> fsteps, csteps;
@@ -809,6 +824,7 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
 int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int slot, mftb200_stream stream) {
     if (!c) return MFTB200_ERR_ARG;
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "encode_frame: not configured");
+    if (c->poisoned) return c->fail(MFTB200_ERR_DEVICE_FLAG, "encode_frame: a kernel aborted earlier; call mftb200_configure again");
     if (!bgr || slot < 0 || slot >= c->n_slots) return c->fail(MFTB200_ERR_ARG, "encode_frame: bad slot %d", slot);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     c->last_main = s;
@@ -818,6 +834,7 @@ int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int 
     if (cudaMemcpyAsync(c->frame_u8, bgr, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s) !=
         cudaSuccess)
         return c->fail(MFTB200_ERR_CUDA, "encode_frame: frame copy failed");
+    cudaEventRecord(c->ev_frame_copied, s);
     c->cur_slot = slot;
     if (!c->defer_context || c->profile) {
         // everything queued on ctx_stream so far has to be done with cnet's buffers before the side stream reuses them
@@ -845,6 +862,20 @@ int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int 
     return MFTB200_OK;
 }
 
+int mftb200_slot_buffers(mftb200_ctx* c, void** fmap, void** net, void** inp, size_t* slot_bytes, mftb200_stream stream) {
+    if (!c || !fmap || !net || !inp || !slot_bytes) return MFTB200_ERR_ARG;
+    if (!c->configured) return c->fail(MFTB200_ERR_STATE, "slot_buffers: not configured");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the context encoder of the newest frame may still be parked / running on the engine's own stream: `stream` is
+    // ordered behind it, so that a collective enqueued there sees complete slots
+    if (int r = flush_context(c, s, s)) return r;
+    *fmap = c->fmap_slots; *net = c->net_slots; *inp = c->inp_slots;
+    slot_bytes[0] = static_cast<size_t>(c->npx) * 256 * sizeof(__half);
+    slot_bytes[1] = static_cast<size_t>(c->npx) * 128 * sizeof(float);
+    slot_bytes[2] = static_cast<size_t>(c->npx) * 128 * sizeof(__half);
+    return MFTB200_OK;
+}
+
 int mftb200_is_pinned_host(const void* p) {
     if (!p) return 0;
     cudaPointerAttributes at;
@@ -859,6 +890,7 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
                         mftb200_stream stream) {
     if (!c) return MFTB200_ERR_ARG;
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "raft_refine: not configured");
+    if (c->poisoned) return c->fail(MFTB200_ERR_DEVICE_FLAG, "raft_refine: a kernel aborted earlier; call mftb200_configure again");
     if (n_pairs < 1 || n_pairs > c->max_pairs || !left_slots || !right_slots || !out)
         return c->fail(MFTB200_ERR_ARG, "raft_refine: bad arguments");
     int table[2 * MFTB200_MAX_PAIRS];
@@ -968,29 +1000,25 @@ int mftb200_chain_select(int K, const float* const* left, const float* right, fl
     }
     a.right = right; a.out = out; a.index = index; a.K = K; a.H = H; a.W = W;
     a.occlusion_threshold = occlusion_threshold;
-    launch_chain_select(a, static_cast<cudaStream_t>(stream));
-    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+    return launch_chain_select(a, static_cast<cudaStream_t>(stream)) == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
 }
 
 int mftb200_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
                           mftb200_stream stream) {
     if (!flow || !img || !out || C < 1 || H < 2 || W < 2 || (add_flow && C != 2)) return MFTB200_ERR_ARG;
-    launch_warp_backward(flow, img, C, H, W, add_flow, out, static_cast<cudaStream_t>(stream));
-    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+    return launch_warp_backward(flow, img, C, H, W, add_flow, out, static_cast<cudaStream_t>(stream)) == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
 }
 
 int mftb200_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
                           float* out, mftb200_stream stream) {
     if (!field || !points_xy || !out || C < 1 || H < 2 || W < 2 || N < 0) return MFTB200_ERR_ARG;
-    launch_sample_points(field, C, H, W, points_xy, N, add_points, out, static_cast<cudaStream_t>(stream));
-    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+    return launch_sample_points(field, C, H, W, points_xy, N, add_points, out, static_cast<cudaStream_t>(stream)) == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
 }
 
 int mftb200_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
                          float border, float* out, float* counts, mftb200_stream stream) {
     if (!flow || !img || !out || !counts || C < 1 || H < 1 || W < 1) return MFTB200_ERR_ARG;
-    launch_warp_forward(flow, img, mask, C, H, W, use_border, border, out, counts, static_cast<cudaStream_t>(stream));
-    return cudaGetLastError() == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
+    return launch_warp_forward(flow, img, mask, C, H, W, use_border, border, out, counts, static_cast<cudaStream_t>(stream)) == cudaSuccess ? MFTB200_OK : MFTB200_ERR_CUDA;
 }
 
 int mftb200_device_error_flag(mftb200_ctx* c) {
@@ -999,11 +1027,35 @@ int mftb200_device_error_flag(mftb200_ctx* c) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return c->fail(MFTB200_ERR_CUDA, "device error: %s", cudaGetErrorString(e));
     cudaMemcpy(&v, c->err_flag, sizeof v, cudaMemcpyDeviceToHost);
-    if (v != 0) {
-        cudaMemset(c->err_flag, 0, sizeof v);
-        return c->fail(MFTB200_ERR_DEVICE_FLAG, "a kernel reported a pipeline time-out (warp role %d)", v - 1);
+    if (v != 0 || c->poisoned) {
+        // The aborted launch left the program kernels' queue counters and arrival sets out of step with the host-side
+        // bases: nothing may be launched on this workspace again.  mftb200_configure rebuilds it (and clears the flag).
+        c->poisoned = true;
+        return c->fail(MFTB200_ERR_DEVICE_FLAG, "a kernel reported a pipeline time-out (warp role %d); reconfigure before further use", v - 1);
     }
     return 0;
+}
+
+int mftb200_error_flag_async(mftb200_ctx* c, mftb200_stream stream) {
+    if (!c) return MFTB200_ERR_ARG;
+    return cudaMemcpyAsync(c->err_host, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)) == cudaSuccess
+               ? MFTB200_OK : c->fail(MFTB200_ERR_CUDA, "error_flag_async: copy failed");
+}
+
+int mftb200_error_flag_poll(mftb200_ctx* c) {
+    if (!c) return MFTB200_ERR_ARG;
+    if (c->poisoned) return c->fail(MFTB200_ERR_DEVICE_FLAG, "a kernel aborted earlier; reconfigure before further use");
+    const int v = *static_cast<volatile int*>(c->err_host);
+    if (v != 0) {
+        c->poisoned = true;
+        return c->fail(MFTB200_ERR_DEVICE_FLAG, "a kernel reported a pipeline time-out (warp role %d); reconfigure before further use", v - 1);
+    }
+    return MFTB200_OK;
+}
+
+int mftb200_wait_frame_copied(mftb200_ctx* c) {
+    if (!c) return MFTB200_ERR_ARG;
+    return cudaEventSynchronize(c->ev_frame_copied) == cudaSuccess ? MFTB200_OK : c->fail(MFTB200_ERR_CUDA, "wait_frame_copied: device error");
 }
 
 int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {

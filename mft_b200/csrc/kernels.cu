@@ -17,7 +17,7 @@ __device__ __forceinline__ void pdl_enter() {
 }
 
 template <class... KArgs, class... Args>
-static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -28,7 +28,7 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ==========================================================================================
@@ -121,11 +121,11 @@ chain_select_kernel(const ChainSelectArgs a, const float sx, const float sy) {
     if (a.index != nullptr) a.index[p] = static_cast<uint8_t>(bidx);
 }
 
-void launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream) {
+cudaError_t launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream) {
     const float sx = static_cast<float>(2.0 / (a.W - 1));
     const float sy = static_cast<float>(2.0 / (a.H - 1));
     dim3 grid((a.W + 255) / 256, a.H);
-    launch_pdl(chain_select_kernel, grid, dim3(256), 0, stream, a, sx, sy);
+    return launch_pdl(chain_select_kernel, grid, dim3(256), 0, stream, a, sx, sy);
 }
 
 // ==========================================================================================
@@ -168,11 +168,12 @@ warp_backward_kernel(const float* __restrict__ flow, const float* __restrict__ i
     }
 }
 
-void launch_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
+cudaError_t launch_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
                           cudaStream_t stream) {
     dim3 grid((W + 255) / 256, H);
     warp_backward_kernel<<<grid, 256, 0, stream>>>(flow, img, C, H, W, add_flow, out, static_cast<float>(2.0 / (W - 1)),
                                                    static_cast<float>(2.0 / (H - 1)));
+    return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
@@ -190,12 +191,13 @@ sample_points_kernel(const float* __restrict__ field, int C, int H, int W, const
     }
 }
 
-void launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
+cudaError_t launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
                           float* out, cudaStream_t stream) {
-    if (N <= 0) return;
+    if (N <= 0) return cudaSuccess;
     sample_points_kernel<<<(N + 255) / 256, 256, 0, stream>>>(field, C, H, W, points_xy, N, add_points, out,
                                                               static_cast<float>(2.0 / (W - 1)),
                                                               static_cast<float>(2.0 / (H - 1)));
+    return cudaGetLastError();
 }
 
 // ==========================================================================================
@@ -240,13 +242,15 @@ splat_normalize_kernel(float* __restrict__ out, const float* __restrict__ counts
     out[i] = n > 0.0f ? out[i] / n : (use_border ? border : out[i]);
 }
 
-void launch_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
+cudaError_t launch_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
                          float border, float* out, float* counts, cudaStream_t stream) {
     const long cells = static_cast<long>(H) * W;
-    cudaMemsetAsync(out, 0, sizeof(float) * cells * C, stream);
-    cudaMemsetAsync(counts, 0, sizeof(float) * cells, stream);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * cells * C, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, sizeof(float) * cells, stream);
+    if (e != cudaSuccess) return e;
     splat_scatter_kernel<<<dim3((W + 255) / 256, H), 256, 0, stream>>>(flow, img, mask, C, H, W, out, counts);
     splat_normalize_kernel<<<static_cast<unsigned>((cells * C + 255) / 256), 256, 0, stream>>>(out, counts, C, cells, use_border, border);
+    return cudaGetLastError();
 }
 
 // ==========================================================================================
@@ -292,10 +296,10 @@ frame_patches_kernel(const uint8_t* __restrict__ bgr, int H, int W, int Hp, int 
                    *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
 }
 
-void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
+cudaError_t launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
                           cudaStream_t stream) {
     const long total8 = static_cast<long>(Hp / 2) * (Wp / 2) * 19;
-    launch_pdl(frame_patches_kernel, dim3(static_cast<unsigned>((total8 + 255) / 256)), dim3(256), 0, stream, bgr, H, W, Hp,
+    return launch_pdl(frame_patches_kernel, dim3(static_cast<unsigned>((total8 + 255) / 256)), dim3(256), 0, stream, bgr, H, W, Hp,
                Wp, pad_left, pad_top, patches, total8);
 }
 
@@ -336,11 +340,11 @@ instnorm_stats_kernel(const __half* __restrict__ raw, int P, int C, int pix_per_
     }
 }
 
-void launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums, cudaStream_t stream) {
-    cudaMemsetAsync(sums, 0, sizeof(double) * B * 2 * C, stream);
+cudaError_t launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums, cudaStream_t stream) {
+    if (cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * B * 2 * C, stream)) return e;
     const int pix_per_block = 256;
     dim3 grid((P + pix_per_block - 1) / pix_per_block, B);
-    launch_pdl(instnorm_stats_kernel, grid, dim3(kStatThreads), 0, stream, raw, P, C, pix_per_block, sums);
+    return launch_pdl(instnorm_stats_kernel, grid, dim3(kStatThreads), 0, stream, raw, P, C, pix_per_block, sums);
 }
 
 // 16-byte accesses: one thread = 8 consecutive channels of one pixel (C % 8 == 0: 64 / 96 / 128), two per thread
@@ -409,10 +413,10 @@ instnorm_apply_kernel(const uint4* __restrict__ raw, const double* __restrict__ 
     }
 }
 
-void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
+cudaError_t launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
                            __half* out, cudaStream_t stream) {
     const long total8 = static_cast<long>(B) * P * C / 8;
-    launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total8 + 511) / 512)), dim3(256), 0, stream,
+    return launch_pdl(instnorm_apply_kernel, dim3(static_cast<unsigned>((total8 + 511) / 512)), dim3(256), 0, stream,
                reinterpret_cast<const uint4*>(raw), sums, P, C, relu, reinterpret_cast<const uint4*>(res),
                reinterpret_cast<uint4*>(out), total8);
 }
@@ -448,9 +452,9 @@ pair_setup_kernel(const PairSetup a) {
     if (lane < 2) a.coords1[pp * 2 + lane] = static_cast<float>(lane == 0 ? n % a.w : n / a.w);
 }
 
-void launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
+cudaError_t launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    launch_pdl(pair_setup_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
+    return launch_pdl(pair_setup_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -513,14 +517,14 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
     }
 }
 
-void launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream) {
+cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (static_cast<size_t>(h / 2) * (w / 2) + static_cast<size_t>(h / 4) * (w / 4));
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (cudaError_t e = cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) return e;
         attr = true;
     }
-    launch_pdl(corr_pool_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), smem, stream, L0, L1, L2, L3, h, w);
+    return launch_pdl(corr_pool_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), smem, stream, L0, L1, L2, L3, h, w);
 }
 
 // ==========================================================================================
@@ -559,10 +563,10 @@ lookup_kernel(const LookupArgs a) {
     }
 }
 
-void launch_lookup(const LookupArgs& a, cudaStream_t stream) {
+cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
     const long per_block = 8 * kLkPixPerWarp;
-    launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + per_block - 1) / per_block)), dim3(256), 0, stream, a);
+    return launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + per_block - 1) / per_block)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -602,9 +606,9 @@ ou_pack_kernel(const OuPackArgs a) {
     }
 }
 
-void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
+cudaError_t launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    launch_pdl(ou_pack_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
+    return launch_pdl(ou_pack_kernel, dim3(static_cast<unsigned>((total + 7) / 8)), dim3(256), 0, stream, a);
 }
 
 // ==========================================================================================
@@ -682,9 +686,9 @@ upsample_kernel(const UpsampleArgs a) {
     o[3 * hw] = sqrtf(expf(acc[4]));
 }
 
-void launch_upsample(const UpsampleArgs& a, cudaStream_t stream) {
+cudaError_t launch_upsample(const UpsampleArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    launch_pdl(upsample_kernel, dim3(static_cast<unsigned>((total + 3) / 4)), dim3(256), 0, stream, a);
+    return launch_pdl(upsample_kernel, dim3(static_cast<unsigned>((total + 3) / 4)), dim3(256), 0, stream, a);
 }
 
 }  // namespace mftb

@@ -1,5 +1,6 @@
 // Bandwidth-bound kernels of the MFT hot path (everything that is not an implicit GEMM).
-// Host-callable launchers; all pointers are device pointers; all launches go to `stream`.
+// Host-callable launchers; all pointers are device pointers; all launches go to `stream`; every launcher returns the
+// launch's cudaError_t (checked by the engine).
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
@@ -17,17 +18,17 @@ struct ChainSelectArgs {
     int K, H, W;
     float occlusion_threshold;
 };
-void launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream);
+cudaError_t launch_chain_select(const ChainSelectArgs& a, cudaStream_t stream);
 
 // FlowOUTrackingResult.warp_backward (MFT/results.py:116-136): out[c,y,x] = bilinear(img[c], (x,y)+flow[:,y,x]),
 // zeros outside, align_corners=True, same defined operation order as chain_select.  add_flow=1 turns it into
 // FlowOUTrackingResult.chain (results.py:87-114) for C == 2: out = (p + S) - grid.
-void launch_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
+cudaError_t launch_warp_backward(const float* flow, const float* img, int C, int H, int W, int add_flow, float* out,
                           cudaStream_t stream);
 
 // Bilinear point queries (MFT/results.py:138-188, MFT/utils/interpolation.py:76-94): out[c, i] =
 // bilinear(field[c], points[i]) (+ points[i][c] when add_points, i.e. warp_forward_points).
-void launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
+cudaError_t launch_sample_points(const float* field, int C, int H, int W, const float* points_xy, int N, int add_points,
                           float* out, cudaStream_t stream);
 
 // Forward splat (FlowOUTrackingResult.warp_forward -> interpolation.bilinear_splat, MFT/results.py:190-248,
@@ -35,20 +36,20 @@ void launch_sample_points(const float* field, int C, int H, int W, const float* 
 // (x, y) + flow with the reference's clamped bilinear weights; out = accum / counts where counts > 0, else 0 (or `border`).
 // img / out: (H,W,C) float; mask: (H,W) uint8 or nullptr; counts: (H,W) float scratch.  Accumulation uses float atomics
 // (order is not defined: results agree with the oracle to rounding, not bit for bit).
-void launch_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
+cudaError_t launch_warp_forward(const float* flow, const float* img, const uint8_t* mask, int C, int H, int W, int use_border,
                          float border, float* out, float* counts, cudaStream_t stream);
 
 // uint8 BGR HWC frame -> fp16 im2col patches of the encoders' 7x7 stride-2 first conv,
 // [ (Hp/2)*(Wp/2) ][152], k = (ky*7+kx)*3 + c (c: R,G,B), values 2*(v/255)-1; the frame is
 // replicate-padded to Hp x Wp (pad_left/pad_top) first, the conv itself zero-pads.
-void launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
+cudaError_t launch_frame_patches(const uint8_t* bgr, int H, int W, int Hp, int Wp, int pad_left, int pad_top, __half* patches,
                           cudaStream_t stream);
 
 // Instance norm over raw fp16 conv outputs [B][P][C].
-void launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums /*[B][2][C], zeroed here*/,
+cudaError_t launch_instnorm_stats(const __half* raw, int B, int P, int C, double* sums /*[B][2][C], zeroed here*/,
                            cudaStream_t stream);
 // out = act((raw-mean)*rstd); if res != nullptr: out = relu(res + out).  act = relu if relu else identity.
-void launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
+cudaError_t launch_instnorm_apply(const __half* raw, const double* sums, int B, int P, int C, int relu, const __half* res,
                            __half* out, cudaStream_t stream);
 
 struct PairSetup {
@@ -62,10 +63,10 @@ struct PairSetup {
     float* coords1;                  // [pair][Npx][2]
     int n_pairs, h, w;
 };
-void launch_pair_setup(const PairSetup& a, cudaStream_t stream);
+cudaError_t launch_pair_setup(const PairSetup& a, cudaStream_t stream);
 
 // 2x2 average pooling of the correlation volume over the target dims: L0 [rows][h*w] -> L1..L3.
-void launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream);
+cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream);
 
 struct LookupArgs {
     const __half* lvl[4];            // pyramid levels [pair*Npx + n][h_l*w_l], fp16
@@ -75,14 +76,14 @@ struct LookupArgs {
     __half* X;                       // writes flow into X[:, 382:384]
     int n_pairs, h, w;
 };
-void launch_lookup(const LookupArgs& a, cudaStream_t stream);
+cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream);
 
 struct OuPackArgs {
     const __half* X; const __half* corr16; const float* coords1; const float* delta32;
     __half* packed;                  // [pair*Npx][720]
     int n_pairs, h, w;
 };
-void launch_ou_pack(const OuPackArgs& a, cudaStream_t stream);
+cudaError_t launch_ou_pack(const OuPackArgs& a, cudaStream_t stream);
 
 struct UpsampleArgs {
     const float* mask32;             // [pair*Npx][576]
@@ -91,6 +92,6 @@ struct UpsampleArgs {
     float* out;                      // planar (pairs,4,H,W): fx, fy, occlusion prob, sigma
     int n_pairs, h, w, H, W, pad_left, pad_top;
 };
-void launch_upsample(const UpsampleArgs& a, cudaStream_t stream);
+cudaError_t launch_upsample(const UpsampleArgs& a, cudaStream_t stream);
 
 }  // namespace mftb

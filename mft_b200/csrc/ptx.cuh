@@ -45,12 +45,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a broken pipeline must never hang the GPU.  Returns false on timeout.
+// Bounded wait: a broken pipeline must never hang the GPU.  Returns false on timeout.  The bound is TIME based (2 s of
+// %globaltimer, far beyond any launch of the path, which last < 1 ms): an iteration count can be exhausted by a healthy
+// pipeline that is merely slow (preemption, time-slicing, a debugger).  The slow path is out of line so that its 64-bit
+// state does not cost the role loops registers.
+constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        for (int i = 0; i < 64; ++i)
+            if (mbar_try_wait(bar, parity)) return true;
+        if (global_timer_ns() - t0 > kWaitTimeoutNs) return false;
+    }
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 20); ++i) {
+    for (uint32_t i = 0; i < 1024u; ++i) {
         if (mbar_try_wait(bar, parity)) return true;
     }
-    return false;
+    return mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- inter-CTA tile flags (persistent program kernel)

@@ -51,23 +51,28 @@ class Engine:
         _lib.check(self.L.mftb200_set_option(self.ctx, key.encode(), int(value)), self.ctx)
 
     def encode_frame(self, frame, slot):
-        """frame: (H,W,3) uint8 BGR numpy array (host) or torch CUDA tensor."""
+        """frame: (H,W,3) uint8 BGR numpy array (host) or torch CUDA tensor.
+
+        A numpy frame in page-locked memory is DMA'd straight from the caller's buffer: the caller must leave it
+        unchanged until ``wait_frame_copied()`` returns (or until a result that depends on the frame is back on the
+        host).  Returns True when that in-place path was taken."""
         H, W = self.geometry[:2]
         if isinstance(frame, torch.Tensor) and frame.is_cuda:
             assert frame.dtype == torch.uint8 and tuple(frame.shape) == (H, W, 3) and frame.is_contiguous()
             _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(frame.data_ptr()), 1, slot, _stream_ptr()), self.ctx)
-            return
+            return False
         frame = np.asarray(frame)
         assert frame.dtype == np.uint8 and frame.shape == (H, W, 3), (frame.dtype, frame.shape)
         if frame.flags.c_contiguous and self.L.mftb200_is_pinned_host(C.c_void_p(frame.ctypes.data)):
             # the caller's frame is page-locked: DMA straight from it (the caller keeps it unchanged until the result of this
             # frame is back, like the reference, whose memory holds references to the caller's frames, MFT.py:150)
             _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(frame.ctypes.data), 0, slot, _stream_ptr()), self.ctx)
-            return
+            return True
         # stage through pinned memory so the H2D copy is asynchronous w.r.t. the host
         torch.cuda.current_stream().synchronize()
         self._pinned.numpy()[...] = frame
         _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(self._pinned.data_ptr()), 0, slot, _stream_ptr()), self.ctx)
+        return False
 
     def refine(self, left_slots, right_slots, out=None):
         """Batched RAFT-OU refinement.  Returns CUDA float tensor (n_pairs, 4, H, W)."""
@@ -81,8 +86,48 @@ class Engine:
         _lib.check(self.L.mftb200_raft_refine(self.ctx, n, ls, rs, C.c_void_p(out.data_ptr()), _stream_ptr()), self.ctx)
         return out
 
+    def slot_tensors(self):
+        """Zero-copy torch views of the feature-slot arrays (fmap fp16 [S,N,256], net fp32 [S,N,128], inp fp16 [S,N,128]) for
+        multi-GPU feature exchange; work enqueued on the current stream afterwards sees all earlier encodes complete."""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        nbytes = (C.c_size_t * 3)()
+        _lib.check(self.L.mftb200_slot_buffers(self.ctx, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(ptrs[2]), nbytes, _stream_ptr()), self.ctx)
+        S = self.geometry[3]
+        out = []
+        for p, nb, (ch, dt, ts) in zip(ptrs, nbytes, ((256, torch.float16, '<f2'), (128, torch.float32, '<f4'), (128, torch.float16, '<f2'))):
+            n = nb // (ch * (2 if dt == torch.float16 else 4))
+
+            class _Mem:          # __cuda_array_interface__ carrier: torch.as_tensor wraps the memory without a copy
+                pass
+            m = _Mem()
+            m.__cuda_array_interface__ = {'shape': (S, n, ch), 'typestr': ts, 'data': (p.value, False), 'version': 2, 'strides': None}
+            t = torch.as_tensor(m, device='cuda')
+            t._mftb200_owner = self       # the engine owns the memory
+            out.append(t)
+        return out
+
     def check_device(self):
-        _lib.check(self.L.mftb200_device_error_flag(self.ctx), self.ctx)
+        """Synchronises the device and raises if a kernel reported a pipeline time-out."""
+        self._checked(self.L.mftb200_device_error_flag(self.ctx))
+
+    def error_flag_async(self):
+        """Enqueues a copy of the device error flag into its pinned mirror on the current stream (no sync)."""
+        _lib.check(self.L.mftb200_error_flag_async(self.ctx, _stream_ptr()), self.ctx)
+
+    def error_flag_poll(self):
+        """Raises if the mirror shows an aborted kernel (as of the last error_flag_async the stream has completed)."""
+        self._checked(self.L.mftb200_error_flag_poll(self.ctx))
+
+    def wait_frame_copied(self):
+        """Blocks until the newest encode_frame's host->device copy has left the caller's buffer."""
+        _lib.check(self.L.mftb200_wait_frame_copied(self.ctx), self.ctx)
+
+    def _checked(self, code):
+        if code != 0:
+            # an aborted launch leaves the persistent kernels' work queues undefined: the library refuses further launches
+            # until the workspace is rebuilt, so the next configure() must not be skipped as "same geometry"
+            self.geometry = None
+        _lib.check(code, self.ctx)
 
     def profile_fetch(self):
         """(ms, steps) per kind: index 0 = tensor-core conv launches, 1 = bandwidth-bound kernels."""

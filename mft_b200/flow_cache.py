@@ -42,7 +42,12 @@ class DeviceFlowCache:
         """Stores a copy (io.py:674-698): the caller may reuse its tensors."""
         key = (int(left_id), int(right_id))
         packed = torch.cat([flow.reshape(2, *flow.shape[-2:]), occlusion.reshape(1, *flow.shape[-2:]),
-                            sigma.reshape(1, *flow.shape[-2:])], 0).to(device=self.device, dtype=self.dtype).contiguous()
+                            sigma.reshape(1, *flow.shape[-2:])], 0).to(device=self.device)
+        if self.dtype == torch.float16:
+            # fp16 storage: flow resolution is 2^-10 relative (0.25 px at 256..512 px of motion, 0.03 px below 32 px),
+            # sigma = sqrt(exp(u)) of a large predicted log-variance would overflow to inf: saturate at the fp16 maximum
+            packed = packed.clamp(min=-65504.0, max=65504.0)
+        packed = packed.to(dtype=self.dtype).contiguous()
         old = self.store.pop(key, None)
         if old is not None:
             self.bytes -= old.numel() * old.element_size()

@@ -35,13 +35,27 @@ class RAFTWrapper:
         model = config.model
         state = model if isinstance(model, dict) else _weights.load_checkpoint(str(model))
         self.iters = int(config.flow_iters) if config.flow_iters else 12
-        self.engine = Engine(state)
-        self.model = self.engine          # the reference exposes the network as .model (raft.py:28)
+        self._state = state
+        self.engine = Engine(state)       # the tracker's engine: its feature slots mirror MFT.memory
+        self._flow_engine = None          # stand-alone compute_flow calls of another geometry get their own workspace
+        self._claimed = None              # geometry a tracker holds live feature slots for
+        self.model = self.engine          # the reference exposes the network as .model (raft.py:28); here: the engine handle
         self.last_flow_shape = None
 
-    def ensure_geometry(self, H, W):
-        self.engine.configure(H, W, max_pairs=MAX_PAIRS, n_slots=N_SLOTS, iters=self.iters)
-        return self.engine
+    def ensure_geometry(self, H, W, claim=False):
+        """Engine configured for H x W frames.  claim=True (MFT.init): the tracker's engine, (re)configured freely --
+        init resets all tracker state anyway.  Otherwise (compute_flow): the tracker's engine only if it already has
+        this geometry; a different size goes to a second engine, because reconfiguring would zero the feature slots
+        a running track depends on (the reference's compute_flow is stateless)."""
+        if claim or self._claimed is None or self._claimed == (H, W):
+            self.engine.configure(H, W, max_pairs=MAX_PAIRS, n_slots=N_SLOTS, iters=self.iters)
+            if claim:
+                self._claimed = (H, W)
+            return self.engine
+        if self._flow_engine is None:
+            self._flow_engine = Engine(self._state)
+        self._flow_engine.configure(H, W, max_pairs=1, n_slots=2, iters=self.iters)
+        return self._flow_engine
 
     def compute_flow(self, src_img, dst_img, mode='TC', vis=False, src_img_identifier=None,
                      numpy_out=False, init_flow=None, vis_debug=False):
@@ -50,9 +64,14 @@ class RAFTWrapper:
             raise NotImplementedError('init_flow is never used by the tracker (MFT.py:98) and is not supported')
         H, W = src_img.shape[:2]
         eng = self.ensure_geometry(H, W)
-        eng.encode_frame(src_img, TRACKER_SLOTS)
-        eng.encode_frame(dst_img, TRACKER_SLOTS + 1)
-        out = eng.refine([TRACKER_SLOTS], [TRACKER_SLOTS + 1])[0]
+        s0 = TRACKER_SLOTS if eng is self.engine else 0        # the two scratch slots behind the tracker's ring
+        in_place = eng.encode_frame(src_img, s0)
+        in_place = eng.encode_frame(dst_img, s0 + 1) or in_place
+        out = eng.refine([s0], [s0 + 1])[0]
+        eng.error_flag_async()
+        if in_place:
+            eng.wait_frame_copied()
+        eng.error_flag_poll()
         flow, occlusions, sigma = out[0:2], out[2:3], out[3:4]
         extra = {'occlusion': occlusions, 'sigma': sigma, 'debug': None}
         if mode == 'flow':

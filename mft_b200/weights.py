@@ -35,7 +35,8 @@ def strip_module_prefix(state_dict):
 
 
 def load_checkpoint(path):
-    return strip_module_prefix(torch.load(path, map_location='cpu'))
+    # weights_only: a checkpoint is data from an untrusted source -- never unpickle arbitrary objects
+    return strip_module_prefix(torch.load(path, map_location='cpu', weights_only=True))
 
 
 def _pack(w, b, cout_pad=None):
@@ -115,3 +116,87 @@ def pack_all(W):
     out.append(_pack(w2, torch.cat([bo2, bu2], 0), cout_pad=16))
     assert len(out) == 47
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weights without the oracle: checkpoint discovery and a random initialisation of the architecture (benchmarks)
+# ------------------------------------------------------------------------------------------------------------------
+CKPT_NAME = 'raft-things-sintel-kubric-splitted-occlusion-uncertainty-non-occluded-base-sintel.pth'
+
+
+def find_checkpoint():
+    """Path of the shipped RAFT-OU checkpoint (configs/flow/RAFTou_kubric_huber_split_nonoccl.py:25 of the reference) if it
+    is reachable: $MFT_CHECKPOINT, the copy that travels with the repo snapshot, a reference checkout.  None otherwise."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get('MFT_CHECKPOINT', ''), os.path.join(root, 'oracle', '_ref', 'raft_ou_checkpoint.pth'),
+             os.path.join(os.environ.get('MFT_REFERENCE_ROOT', '/root/reference'), 'checkpoints', CKPT_NAME),
+             os.path.join('checkpoints', CKPT_NAME)]
+    for p in cands:
+        if p and os.path.isfile(p):
+            return p
+    return None
+
+
+def architecture_spec():
+    """(name, shape) of every tensor of the shipped RAFT-OU architecture that the path consumes (SURVEY.md Appendix B;
+    MFT/RAFT/core/{extractor,update,raft}.py)."""
+    spec = []
+
+    def conv(name, co, ci, kh, kw):
+        spec.extend([(name + '.weight', (co, ci, kh, kw)), (name + '.bias', (co,))])
+
+    def bn(name, c):
+        spec.extend([(f'{name}.{s}', (c,)) for s in ('weight', 'bias', 'running_mean', 'running_var')])
+
+    for net in ('fnet', 'cnet'):
+        norm = bn if net == 'cnet' else (lambda name, c: None)
+        norm(f'{net}.norm1', 64)
+        conv(f'{net}.conv1', 64, 3, 7, 7)
+        cin = 64
+        for li, dim in ((1, 64), (2, 96), (3, 128)):
+            for bi in (0, 1):
+                p = f'{net}.layer{li}.{bi}'
+                conv(p + '.conv1', dim, cin if bi == 0 else dim, 3, 3)
+                conv(p + '.conv2', dim, dim, 3, 3)
+                norm(p + '.norm1', dim)
+                norm(p + '.norm2', dim)
+                if bi == 0 and li > 1:
+                    norm(p + '.norm3', dim)
+                    conv(p + '.downsample.0', dim, cin, 1, 1)
+            cin = dim
+        conv(f'{net}.conv2', 256, 128, 1, 1)
+    ub, ob = 'update_block.', 'occlusion_block.'
+    for name, co, ci, kh, kw in (('encoder.convc1', 256, 324, 1, 1), ('encoder.convc2', 192, 256, 3, 3), ('encoder.convf1', 128, 2, 7, 7),
+                                 ('encoder.convf2', 64, 128, 3, 3), ('encoder.conv', 126, 256, 3, 3),
+                                 ('gru.convz1', 128, 384, 1, 5), ('gru.convr1', 128, 384, 1, 5), ('gru.convq1', 128, 384, 1, 5),
+                                 ('gru.convz2', 128, 384, 5, 1), ('gru.convr2', 128, 384, 5, 1), ('gru.convq2', 128, 384, 5, 1),
+                                 ('flow_head.conv1', 256, 128, 3, 3), ('flow_head.conv2', 2, 256, 3, 3), ('mask.0', 256, 128, 3, 3),
+                                 ('mask.2', 576, 256, 1, 1)):
+        conv(ub + name, co, ci, kh, kw)
+    for name, co, ci in (('occl_head.conv1', 128, 712), ('occl_head.conv2', 2, 128), ('uncertainty_head.conv1', 128, 712),
+                         ('uncertainty_head.conv2', 1, 128)):
+        conv(ob + name, co, ci, 3, 3)
+    return spec
+
+
+def random_init(seed=0):
+    """Random weights of the architecture for benchmarks without the checkpoint (fan-in scaled, so activations stay O(1);
+    the recurrent / output convolutions a little smaller so the refinement iterations stay bounded)."""
+    gen = torch.Generator().manual_seed(int(seed))
+    W = {}
+    for name, shape in architecture_spec():
+        if name.endswith('.weight') and len(shape) == 4:
+            gain = (2.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+            gain *= 0.7 if '.gru.' in name else 1.0
+            gain *= 0.25 if name.endswith(('flow_head.conv2.weight', 'head.conv2.weight')) else 1.0
+            W[name] = torch.randn(shape, generator=gen) * gain
+        elif name.endswith('running_var'):
+            W[name] = torch.rand(shape, generator=gen) + 0.5
+        elif name.endswith('running_mean'):
+            W[name] = torch.randn(shape, generator=gen) * 0.1
+        elif name.endswith('.weight'):
+            W[name] = torch.rand(shape, generator=gen) * 0.4 + 0.8
+        else:
+            W[name] = torch.randn(shape, generator=gen) * 0.05
+    return W

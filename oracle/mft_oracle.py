@@ -118,7 +118,7 @@ def seeded_weights(seed=0):
 
 def load_checkpoint(path):
     """Checkpoint loader: strips the DataParallel 'module.' prefix (MFT/raft.py:20-23)."""
-    sd = torch.load(path, map_location='cpu')
+    sd = torch.load(path, map_location='cpu', weights_only=True)
     W = {}
     for k, v in sd.items():
         if k.startswith('module.'):

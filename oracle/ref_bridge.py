@@ -19,7 +19,15 @@ import sys
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get('MFT_REFERENCE_ROOT', '/root/reference')
+def _find_root():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.environ.get('MFT_REFERENCE_ROOT', ''), '/root/reference', os.path.join(here, 'baseline', '_ref')):
+        if p and os.path.isfile(os.path.join(p, 'MFT', 'MFT.py')):
+            return p
+    return os.environ.get('MFT_REFERENCE_ROOT', '/root/reference')
+
+
+REF_ROOT = _find_root()
 CKPT_REL = 'checkpoints/raft-things-sintel-kubric-splitted-occlusion-uncertainty-non-occluded-base-sintel.pth'
 VIDEO_REL = 'demo_in/ugsJtsO9w1A-00.00.24.457-00.00.29.462_HD.mp4'
 
@@ -63,7 +71,7 @@ def build_reference_model(state_dict=None):
     args = AttrDict(occlusion_module='separate_with_uncertainty', small=False, mixed_precision=False)
     model = RAFT(args)
     if state_dict is None:
-        sd = torch.load(os.path.join(REF_ROOT, CKPT_REL), map_location='cpu')
+        sd = torch.load(os.path.join(REF_ROOT, CKPT_REL), map_location='cpu', weights_only=True)
         sd = {k[len('module.'):]: v for k, v in sd.items()}
         model.load_state_dict(sd)
     else:
@@ -101,8 +109,9 @@ class CpuFlower:
         return flow, {'occlusion': occ, 'sigma': sigma, 'debug': None, 'raw': pred}
 
 
-def build_reference_tracker(model, deltas, occlusion_threshold=0.02, iters=12):
-    """The reference MFT tracker class, on CPU, around ``model``."""
+def build_reference_tracker(model, deltas, occlusion_threshold=0.02, iters=12, flower=None):
+    """The reference MFT tracker class, on CPU, around ``model`` (or around ``flower``, any object with the
+    reference's compute_flow(mode='flow') surface, e.g. a recording wrapper of CpuFlower)."""
     ref_mft, _, ref_config, _, _ = _import_reference()
 
     class CpuMFT(ref_mft.MFT):
@@ -114,7 +123,7 @@ def build_reference_tracker(model, deltas, occlusion_threshold=0.02, iters=12):
     C = ref_config.Config()
     C.deltas = list(deltas)
     C.occlusion_threshold = occlusion_threshold
-    return CpuMFT(C, CpuFlower(model, iters))
+    return CpuMFT(C, flower if flower is not None else CpuFlower(model, iters))
 
 
 def demo_frames(n, size=None, start=0):

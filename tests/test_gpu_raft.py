@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden
+from conftest import golden, record_parity
 from oracle import mft_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -95,6 +95,7 @@ def test_flow_real_128_vs_oracle_and_golden(real_weights):
         f, o, s = O.compute_flow(real_weights, frames[a], frames[b])
         for ref in ((f, o, s), tuple(torch.from_numpy(g[f'{k}_{a}_{b}']) for k in ('flow', 'occ', 'sigma'))):
             st = _flow_stats(out[p], *ref)
+            record_parity(f'real128_pair{a}_{b}_vs_' + ('oracle' if ref[0] is f else 'reference'), st)
             assert st['epe_mean'] < 0.05 and st['epe_p995'] < 0.5, st
             assert st['occ_mean'] < 0.01 and st['sigma_rel'] < 0.02, st
 
@@ -110,6 +111,7 @@ def test_config1_real_256(real_weights):
     assert tuple(flow.shape) == (2, 256, 256) and tuple(extra['occlusion'].shape) == (1, 256, 256)
     got = torch.cat([flow, extra['occlusion'], extra['sigma']])
     st = _flow_stats(got, torch.from_numpy(g['flow_0_1']), torch.from_numpy(g['occ_0_1']), torch.from_numpy(g['sigma_0_1']))
+    record_parity('config1_real256_vs_reference', st)
     assert st['epe_mean'] < 0.05 and st['epe_p995'] < 0.5 and st['occ_mean'] < 0.01 and st['sigma_rel'] < 0.02, st
     src, dst, ex = fl.compute_flow(g['frames'][0], g['frames'][1], mode='TC')
     assert tuple(src.shape) == (2, 256 * 256) and torch.allclose(dst - src, flow.reshape(2, -1), atol=1e-4)
@@ -127,6 +129,7 @@ def test_padding_and_ragged_tiles_seeded(size, seeded_weights):
     eng.check_device()
     f, o, s = O.compute_flow(seeded_weights, frames[0], frames[1])
     st = _flow_stats(out[0], f, o, s)
+    record_parity(f'seeded_{H}x{Wd}_vs_oracle', st)
     assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
 
 
@@ -139,6 +142,7 @@ def test_padded_size_vs_reference_golden(seeded_weights):
     out = eng.refine([0], [1])
     eng.check_device()
     st = _flow_stats(out[0], torch.from_numpy(g['flow_0_2']), torch.from_numpy(g['occ_0_2']), torch.from_numpy(g['sigma_0_2']))
+    record_parity('seeded_131x140_vs_reference', st)
     assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
 
 
@@ -264,6 +268,8 @@ def test_tracker_vs_oracle_real_128(real_weights):
         want = np.concatenate(om.result)
         epe = np.sqrt(((got[:2] - want[:2]) ** 2).sum(0))
         agree = (meta.selected_delta_i.cpu().numpy() == om.index).mean()
+        record_parity(f'track128_frame{i}', dict(epe_median=np.median(epe), epe_mean=epe.mean(), epe_p95=np.quantile(epe, 0.95),
+                                                 index_agree=agree, mean_diff=np.abs(got.reshape(4, -1).mean(1) - g['means'][i - 1]).max()))
         # chains multiply small flow differences by selection flips at near-ties: judge the field
         # by robust statistics and the index map by agreement rate
         assert np.median(epe) < 0.05 and np.quantile(epe, 0.95) < 0.5, (i, np.median(epe), np.quantile(epe, 0.95))

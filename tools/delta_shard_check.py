@@ -31,8 +31,8 @@ def main():
     eng.configure(H, W, max_pairs=len(deltas), n_slots=T + 1, iters=12)
     eng.encode_frame(frames[0], 0)
 
-    def flow_fn(t, live):
-        return eng.refine([left for _, left in live], [t] * len(live))
+    def flow_fn(t, live, out):
+        eng.refine([left for _, left in live], [t] * len(live), out=out)      # straight into the gather buffer
 
     def select_fn(lefts, right):
         return E.chain_select(lefts, right, 0.02, want_index=False)[0]

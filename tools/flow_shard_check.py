@@ -29,8 +29,8 @@ def main():
     for i, f in enumerate(frames):          # every rank encodes the (cheap) per-frame features it may need
         eng.encode_frame(f, i)
 
-    def flow_fn(t, live):
-        return eng.refine([left for _, left in live], [t] * len(live))
+    def flow_fn(t, live, out):
+        eng.refine([left for _, left in live], [t] * len(live), out=out)      # straight into the gather buffer
 
     def select_fn(lefts, right):
         return E.chain_select(lefts, right, 0.02, want_index=False)[0]
