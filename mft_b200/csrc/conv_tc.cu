@@ -553,28 +553,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Correlation-pyramid lookup of one tile's 128 pixels by the 8 epilogue warps: 16 pixels per warp, two in flight (2 x 1664 B
-// of the warp's staging area hold their windows).  Out of line: its registers are then allocated apart from the
-// convolution epilogues' (a spill costs an L2 round trip here -- the L1 is carved out for shared memory).
+// Correlation-pyramid lookup of one tile's 128 pixels by the 8 epilogue warps: 16 pixels per warp in groups of kLkGroup
+// consecutive pixels of one tile row (kLkWinFloats floats of the warp's staging area hold a level's windows).  Out of
+// line: its registers are then allocated apart from the convolution epilogues' (a spill costs an L2 round trip here --
+// the L1 is carved out for shared memory).
 __device__ __noinline__ void prog_lookup_tile(const LookupArgs& lk, const ConvGeom& g, float* win, int ew, int lane, int tx,
                                               int ty, int b) {
     const LookupLane t = lookup_lane_init(lane);
-    for (int r = 0; r < 16; r += 2) {
-        long pp[2];
-        int xs[2], ys[2];
-        LookupPixel px[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int row = ew * 16 + r + u;
-            const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & (g.tile_w - 1));
-            xs[u] = x; ys[u] = y;
-            pp[u] = (y < g.H && x < g.W) ? (static_cast<long>(b) * g.H + y) * g.W + x : -1;
-            if (pp[u] >= 0) lookup_gather(lk, t, pp[u], lane, win + u * kLkWinFloats, px[u]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (pp[u] >= 0) lookup_emit(lk, t, pp[u], xs[u], ys[u], lane, win + u * kLkWinFloats, px[u]);
+    for (int r = 0; r < 16; r += kLkGroup) {
+        const int row = ew * 16 + r;                                   // kLkGroup divides the tile width: one tile row per group
+        const int y = ty * g.tile_h + (row >> g.tile_w_log2), x = tx * g.tile_w + (row & (g.tile_w - 1));
+        if (y >= g.H || x >= g.W) continue;
+        const int nvalid = g.W - x < kLkGroup ? g.W - x : kLkGroup;
+        lookup_group(lk, t, (static_cast<long>(b) * g.H + y) * g.W + x, nvalid, lane, win);
         __syncwarp();
     }
 }

@@ -531,41 +531,24 @@ cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L
 // pyramid lookup (core/corr.py:30-51) + flow operands of the motion encoder
 // one warp per (pair, source pixel)
 // ==========================================================================================
-// The per-pixel routine lives in lookup.cuh (shared with the persistent refinement kernel, which can run the same lookup
-// as tiles of its dataflow program).  Here: one warp per kLkPixPerWarp consecutive (pair, source pixel)s whose windows
-// are requested together (the kernel is latency bound: more loads in flight per warp, lane tables set up once).
-constexpr int kLkPixPerWarp = 1;
-
-__global__ void __launch_bounds__(256, 8)      // 32 registers: all 64 warps of the SM resident (the kernel is latency bound)
+// The routine lives in lookup.cuh (shared with the persistent refinement kernel, which can run the same lookup as tiles
+// of its dataflow program).  Here: one warp per group of kLkGroup consecutive (pair, source pixel)s, 8 groups per block.
+__global__ void __launch_bounds__(256, 5)
 lookup_kernel(const LookupArgs a) {
     pdl_enter();
-    __shared__ float win[8][kLkPixPerWarp][kLkWinFloats];
+    __shared__ __align__(16) float win[8][kLkWinFloats];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    const long p0 = (static_cast<long>(blockIdx.x) * 8 + wib) * kLkPixPerWarp;
-    if (p0 >= total) return;
+    const long pp0 = (static_cast<long>(blockIdx.x) * 8 + wib) * kLkGroup;
+    if (pp0 >= total) return;
     const LookupLane t = lookup_lane_init(lane);
-    const int npx = a.h * a.w;
-    const int n0 = static_cast<int>(static_cast<unsigned>(p0) % static_cast<unsigned>(npx));      // total < 2^31 pixels (32-bit remainder)
-    LookupPixel px[kLkPixPerWarp];
-#pragma unroll
-    for (int i = 0; i < kLkPixPerWarp; ++i)
-        if (p0 + i < total) lookup_gather(a, t, p0 + i, lane, win[wib][i], px[i]);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < kLkPixPerWarp; ++i) {
-        if (p0 + i < total) {
-            int n = n0 + i;
-            if (n >= npx) n -= npx;              // first pixel of the next pair
-            const int y = n / a.w;
-            lookup_emit(a, t, p0 + i, n - y * a.w, y, lane, win[wib][i], px[i]);
-        }
-    }
+    const long left = total - pp0;
+    lookup_group(a, t, pp0, left < kLkGroup ? static_cast<int>(left) : kLkGroup, lane, win[wib]);
 }
 
 cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream) {
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    const long per_block = 8 * kLkPixPerWarp;
+    const long per_block = 8 * kLkGroup;
     return launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + per_block - 1) / per_block)), dim3(256), 0, stream, a);
 }
 

@@ -1,58 +1,47 @@
-// Correlation-pyramid lookup of ONE source pixel by ONE warp (core/corr.py:30-51) + the flow operands of the motion
-// encoder.  Shared by lookup_kernel (kernels.cu) and by the persistent refinement kernel (conv_tc.cu), which can run the
-// lookup as tiles of its dataflow program; both must produce the same bits, so the arithmetic below only uses
-// operations the compiler cannot contract differently in the two translation units (explicit fmaf, no a*b+c).
+// Correlation-pyramid lookup (core/corr.py:30-51) + the flow operands of the motion encoder, for a GROUP of kLkGroup
+// consecutive source pixels per warp pass.  Shared by lookup_kernel (kernels.cu) and by the persistent refinement kernel
+// (conv_tc.cu), which can run the lookup as tiles of its dataflow program; both must produce the same bits, so the
+// arithmetic below only uses operations the compiler cannot contract differently in the two translation units
+// (explicit fmaf, no a*b+c).
 //
 // Per level the 81 sample points of a pixel are the 9x9 integer offsets of ONE position, so they share its fractional
 // part and a 10x10 integer neighbourhood of the pixel's correlation row.  The warp evaluates the position once per
-// level (the oracle's round trip on the first sample; the other samples' own round trips differ from "first sample
-// + k" by ~1e-6 px, four orders of magnitude below the fp16 rounding of the output), stages the four neighbourhoods in
-// shared memory (400 loads per pixel instead of 4 x 324) and blends.
+// (pixel, level) (the oracle's round trip on the first sample; the other samples' own round trips differ from "first
+// sample + k" by ~1e-6 px, four orders of magnitude below the fp16 rounding of the output).
 //
-// The kernel is instruction-issue bound (about 1300 instructions per lane and pixel in its first form), so everything
-// that only depends on the lane -- which window elements it fetches, which outputs it blends, which entries of the
-// 7x7 flow patch it writes -- is tabulated once per warp (LookupLane) and reused for every pixel the warp handles.
+// Round 1 ran one pixel per warp, one fp16 element per load and one of the 81 outputs per lane and was instruction-issue
+// bound (808 warp instructions per pixel, 35 us per iteration at 512^2).  Now, level by level for the whole group:
+//   gather   lane task = (pixel, window row, aligned chunk of VEC = 4 | 2 | 1 fp16 elements): 8-byte loads where the
+//            level's width allows it; a chunk lies either wholly inside the map or wholly outside (zero), so there is
+//            no per-element bounds handling; the chunk lands in shared memory as fp32 [pixel][row][16];
+//   blend    lane task = (pixel, output column i): separable -- 10 horizontal lerps H[row] = lerp(W[row][i], W[row][i+1])
+//            down the column, 9 vertical lerps between consecutive rows (171 lerps per pixel and level instead of 243,
+//            2 shared-memory reads per row instead of 4 per output), the column's 9 outputs are consecutive channels
+//            (core/corr.py:37-40: x offset major) and leave as packed fp16 words.
+// The loads of level l+1 are issued before level l is blended, so their latency overlaps the arithmetic.  The blend is
+// bit-identical to the per-output form lerp(lerp(nw, ne), lerp(sw, se)) of round 1.
 #pragma once
 #include "kernels.h"
 
 namespace mftb {
 
-constexpr int kLkWin = 10;
-constexpr int kLkLevelFloats = kLkWin * kLkWin + 4;
-constexpr int kLkWinFloats = 4 * kLkLevelFloats;      // shared-memory floats per pixel in flight
+constexpr int kLkGroup = 4;                              // pixels per warp pass
+constexpr int kLkRowFloats = 16;                         // shared-memory floats per window row (aligned span of the 10 taps)
+constexpr int kLkWinFloats = kLkGroup * 10 * kLkRowFloats;   // one level's windows of a group: 2560 bytes per warp
 
-struct LookupPixel {
-    float wE[4], wS[4];
-    float cx, cy;
-    bool finite;
-};
-
-// Per-lane constants.  Window element e = lane + 32k (k < 4, e < 100) sits at (ey, ex); output o = lane + 32k (k < 3,
-// o < 81) blends the 2x2 window cell at woff = (o % 9) * 10 + o / 9 (x offset index o / 9 = columns, core/corr.py:37-40);
-// flow-patch entry f = lane + 32k (k < 4, f < 98): channel f & 1 of tap (f >> 1) = ky * 7 + kx.
+// Per-lane constants of the 7x7x2 flow patch: entry f = lane + 32k (k < 4, f < 98): channel f & 1 of tap (f >> 1) = ky * 7 + kx.
 struct LookupLane {
-    int ex[4], ey[4];
-    int woff[3];
     int fdx[4], fdy[4];
 };
 
 __device__ __forceinline__ LookupLane lookup_lane_init(int lane) {
-    // e -> e + 32 is (ey + 3, ex + 2), o -> o + 32 is (i + 3, j + 5), tap -> tap + 16 is (ky + 2, kx + 2), each with one carry:
-    // cheaper than a division per entry (the tables are rebuilt for every pixel when a warp handles only one)
+    // tap -> tap + 16 is (ky + 2, kx + 2) with one carry: cheaper than a division per entry
     LookupLane t;
-    int ey = (lane * 26) >> 8, ex = lane - ey * kLkWin;              // lane / 10, lane % 10 (exact for lane < 69)
-    int i = (lane * 57) >> 9, j = lane - i * 9;                        // lane / 9, lane % 9
     const int tap = lane >> 1;
     int ky = (tap * 37) >> 8, kx = tap - ky * 7;                       // tap / 7, tap % 7 (tap < 16)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        t.ex[k] = ex; t.ey[k] = ey;
         t.fdx[k] = kx - 3; t.fdy[k] = ky - 3;
-        if (k < 3) t.woff[k] = j * kLkWin + i;
-        ex += 2; ey += 3;
-        if (ex >= kLkWin) { ex -= kLkWin; ++ey; }
-        j += 5; i += 3;
-        if (j >= 9) { j -= 9; ++i; }
         kx += 2; ky += 2;
         if (kx >= 7) { kx -= 7; ++ky; }
     }
@@ -67,89 +56,193 @@ __device__ __forceinline__ float lk_roundtrip_div(float c, float size_m1) {
     return ((g + 1.0f) * 0.5f) * size_m1;
 }
 
-// Phase 1: request the four 10x10 windows of pixel `pp` (= pair * h*w + n) into `win` (this warp's kLkWinFloats floats).
-// coords1 may have been written earlier in the same launch by another CTA: read through L2.
-__device__ __forceinline__ void lookup_gather(const LookupArgs& a, const LookupLane& t, long pp, int lane, float* win,
-                                              LookupPixel& px) {
-    const float2 c = __ldcg(reinterpret_cast<const float2*>(a.coords1 + pp * 2));
-    px.cx = c.x;
-    px.cy = c.y;
-    px.finite = isfinite(c.x) && isfinite(c.y);
-    // lane l & 3 evaluates level l & 3 (position round trip, fractions, window origin); the level loop then only
-    // broadcasts the four numbers instead of every lane redoing all four levels
-    const int myl = lane & 3;
-    const int mh = a.h >> myl, mw = a.w >> myl;
-    const float inv = 1.0f / static_cast<float>(1 << myl);          // 1 / 2^level: exact
+// Loads of one level for the group: up to kRounds chunks per lane, kept in registers until lookup_store_level.
+template <int VEC>
+struct LkChunks {
+    static constexpr int kPerRow = VEC == 4 ? 4 : (VEC == 2 ? 6 : 10);          // aligned chunks covering the 10 taps of a row
+    static constexpr int kTasks = kLkGroup * 10 * kPerRow;
+    static constexpr int kRounds = (kTasks + 31) / 32;
+    static constexpr int kWords = VEC == 4 ? 2 : 1;                             // 32-bit registers per chunk
+};
+// One register file for the three widths (a level uses exactly one of them): 13 words cover the worst case (VEC = 1).
+struct LkRegs {
+    unsigned w[13];
+};
+
+// Issues the loads of level `l`.  lane (p * 4 + l) holds X0 / Y0 of (pixel p, level l).
+template <int VEC>
+__device__ __forceinline__ void lookup_load_level(const __half* __restrict__ lvl, int hl, int wl, long pp0, unsigned valid_mask, int l,
+                                                  int myX0, int myY0, int lane, LkRegs& c) {
+    using C = LkChunks<VEC>;
+    const long img = static_cast<long>(hl) * wl;
+#pragma unroll
+    for (int r = 0; r < C::kRounds; ++r) {
+        const int T = r * 32 + lane;
+        int p = T / (10 * C::kPerRow);
+        const int t = T - p * (10 * C::kPerRow);
+        const int row = t / C::kPerRow, ch = t - row * C::kPerRow;
+        p = p < kLkGroup ? p : kLkGroup - 1;                                    // (tail lanes of the last round: clamped, masked below)
+        const int X0 = __shfl_sync(0xffffffffu, myX0, p * 4 + l), Y0 = __shfl_sync(0xffffffffu, myY0, p * 4 + l);
+        const int a = VEC == 4 ? (X0 & ~3) : (VEC == 2 ? (X0 & ~1) : X0);
+        const int gx = a + ch * VEC, gy = Y0 + row;
+        const bool inside = T < C::kTasks && ((valid_mask >> p) & 1u) && static_cast<unsigned>(gx) < static_cast<unsigned>(wl) &&
+                            static_cast<unsigned>(gy) < static_cast<unsigned>(hl);
+        uint2 v = make_uint2(0u, 0u);
+        if (inside) {
+            const __half* q = lvl + (pp0 + p) * img + (gy * wl + gx);
+            if constexpr (VEC == 4) v = __ldg(reinterpret_cast<const uint2*>(q));
+            else if constexpr (VEC == 2) v.x = __ldg(reinterpret_cast<const unsigned*>(q));
+            else v.x = __ldg(reinterpret_cast<const unsigned short*>(q));
+        }
+        c.w[r * C::kWords] = v.x;
+        if constexpr (VEC == 4) c.w[r * C::kWords + 1] = v.y;
+    }
+}
+
+// Converts the chunks to fp32 and stores them into the group's window buffer [pixel][row][16].
+template <int VEC>
+__device__ __forceinline__ void lookup_store_level(const LkRegs& c, int lane, float* win) {
+    using C = LkChunks<VEC>;
+#pragma unroll
+    for (int r = 0; r < C::kRounds; ++r) {
+        const int T = r * 32 + lane;
+        if (T < C::kTasks) {
+            const int p = T / (10 * C::kPerRow);
+            const int t = T - p * (10 * C::kPerRow);
+            const int row = t / C::kPerRow, ch = t - row * C::kPerRow;
+            float* dst = win + (p * 10 + row) * kLkRowFloats + ch * VEC;
+            if constexpr (VEC == 4) {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[2 * r]));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[2 * r + 1]));
+                *reinterpret_cast<float4*>(dst) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            } else if constexpr (VEC == 2) {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[r]));
+                *reinterpret_cast<float2*>(dst) = f0;
+            } else {
+                const unsigned short h = static_cast<unsigned short>(c.w[r]);
+                dst[0] = __half2float(*reinterpret_cast<const __half*>(&h));
+            }
+        }
+    }
+}
+
+// Blends level `l` of the group out of `win` and writes channels [81 l, 81 l + 81) of corr16.
+// lane (p * 4 + l) holds wE / wS / the window's column offset within its aligned span / finiteness of (pixel p, level l).
+__device__ __forceinline__ void lookup_blend_level(__half* __restrict__ corr16, long pp0, unsigned valid_mask, int l, float my_wE, float my_wS,
+                                                   int my_off, int my_finite, int lane, const float* win) {
+#pragma unroll
+    for (int r = 0; r < (kLkGroup * 9 + 31) / 32; ++r) {
+        const int T = r * 32 + lane;
+        int p = (T * 57) >> 9;                               // T / 9 (T < 64)
+        const int i = T - p * 9;
+        const bool active = T < kLkGroup * 9 && ((valid_mask >> (p < kLkGroup ? p : 0)) & 1u);
+        p = p < kLkGroup ? p : kLkGroup - 1;
+        const int src = p * 4 + l;
+        const float wE = __shfl_sync(0xffffffffu, my_wE, src), wS = __shfl_sync(0xffffffffu, my_wS, src);
+        const int off = __shfl_sync(0xffffffffu, my_off, src), fin = __shfl_sync(0xffffffffu, my_finite, src);
+        if (!active) continue;
+        const float* q = win + p * 10 * kLkRowFloats + off + i;
+        float o[9];
+        float prev = 0.0f;
+#pragma unroll
+        for (int row = 0; row < 10; ++row) {
+            const float vw = q[row * kLkRowFloats], ve = q[row * kLkRowFloats + 1];
+            const float h = fmaf(wE, ve - vw, vw);
+            if (row > 0) o[row - 1] = fin ? fmaf(wS, h - prev, prev) : NAN;
+            prev = h;
+        }
+        // channels 81 l + 9 i + (0..8): 18 bytes at a 2-byte aligned offset -> 4-byte words plus one leading / trailing half
+        __half* dst = corr16 + (pp0 + p) * 328 + (l * 81 + i * 9);
+        if (((l + i) & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<__half2*>(dst + 2 * k) = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+            dst[8] = __float2half_rn(o[8]);
+        } else {
+            dst[0] = __float2half_rn(o[0]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<__half2*>(dst + 1 + 2 * k) = __floats2half2_rn(o[1 + 2 * k], o[2 + 2 * k]);
+        }
+    }
+}
+
+// One level: store its chunks, (issue the next level's loads by the caller), blend.  Dispatch on the level's vector width.
+__device__ __forceinline__ int lookup_vec(int wl) { return (wl & 3) == 0 ? 4 : ((wl & 1) == 0 ? 2 : 1); }
+
+// The whole lookup of pixels pp0 .. pp0 + nvalid - 1 (global pixel indices pair * h*w + n; nvalid <= kLkGroup) by one warp.
+// `win`: this warp's kLkWinFloats floats of shared memory.  coords1 may have been written earlier in the same launch by
+// another CTA: read through L2.
+__device__ __forceinline__ void lookup_group(const LookupArgs& a, const LookupLane& t, long pp0, int nvalid, int lane, float* win) {
+    const unsigned valid_mask = (1u << nvalid) - 1u;
+    const int npx = a.h * a.w;
+    // ---- set-up: lane p * 4 + l evaluates (pixel p, level l): position round trip, fractions, window origin -------------------
+    const int sp = (lane >> 2) & (kLkGroup - 1), sl = lane & 3;
+    const bool sv = sp < nvalid;
+    const long spp = pp0 + (sv ? sp : 0);
+    const float2 c = __ldcg(reinterpret_cast<const float2*>(a.coords1 + spp * 2));
+    const int my_finite = (isfinite(c.x) && isfinite(c.y)) ? 1 : 0;
+    const int mh = a.h >> sl, mw = a.w >> sl;
+    const float inv = 1.0f / static_cast<float>(1 << sl);            // 1 / 2^level: exact
     const float fxp = lk_roundtrip_div(c.x * inv - 4.0f, static_cast<float>(mw - 1));
     const float fyp = lk_roundtrip_div(c.y * inv - 4.0f, static_cast<float>(mh - 1));
     const float fx = floorf(fxp), fy = floorf(fyp);
     const float my_wE = fxp - fx, my_wS = fyp - fy;
     // non-finite coordinates: park the window outside the map, every tap then reads as zero (the output is NaN anyway)
-    const int my_X0 = px.finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(mw + 16))) : -64;
-    const int my_Y0 = px.finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(mh + 16))) : -64;
-    int hl = a.h, wl = a.w;
+    const int my_X0 = my_finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(mw + 16))) : -64;
+    const int my_Y0 = my_finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(mh + 16))) : -64;
+    const int vec_mine = lookup_vec(mw);
+    const int my_off = my_X0 - (vec_mine == 4 ? (my_X0 & ~3) : (vec_mine == 2 ? (my_X0 & ~1) : my_X0));
+
+    // ---- levels: the loads of level l + 1 are in flight while level l is blended -------------------------------------------------
+    // (the three vector widths are separate instantiations; a level's width is warp-uniform)
+    LkRegs regs;
+    auto load = [&](int l) {
+        const int hl = a.h >> l, wl = a.w >> l;
+        const int v = lookup_vec(wl);
+        if (v == 4) lookup_load_level<4>(a.lvl[l], hl, wl, pp0, valid_mask, l, my_X0, my_Y0, lane, regs);
+        else if (v == 2) lookup_load_level<2>(a.lvl[l], hl, wl, pp0, valid_mask, l, my_X0, my_Y0, lane, regs);
+        else lookup_load_level<1>(a.lvl[l], hl, wl, pp0, valid_mask, l, my_X0, my_Y0, lane, regs);
+    };
+    auto store = [&](int l) {
+        const int v = lookup_vec(a.w >> l);
+        if (v == 4) lookup_store_level<4>(regs, lane, win);
+        else if (v == 2) lookup_store_level<2>(regs, lane, win);
+        else lookup_store_level<1>(regs, lane, win);
+    };
+    load(0);
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        px.wE[l] = __shfl_sync(0xffffffffu, my_wE, l);
-        px.wS[l] = __shfl_sync(0xffffffffu, my_wS, l);
-        const int X0 = __shfl_sync(0xffffffffu, my_X0, l), Y0 = __shfl_sync(0xffffffffu, my_Y0, l);
-        const __half* base = a.lvl[l] + pp * static_cast<long>(hl * wl);
-        asm volatile("" : "+l"(base));       // keep the row pointer in registers (else it is re-derived from pp for every tap)
-        // unconditional loads (taps outside the map read element 0 and are zeroed afterwards): the address of a predicated
-        // load is recomputed under its predicate, which tripled the integer work of this loop
+        __syncwarp();                      // the previous level's blend is done with the buffer
+        store(l);
+        if (l < 3) load(l + 1);
+        __syncwarp();
+        lookup_blend_level(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
+    }
+    // ---- per pixel: zero pad of corr16, the 7x7x2 zero-padded flow neighbourhood for convf1 (flow = coords1 - coords0,
+    //      core/raft.py:179) and the flow channels of the GRU record ------------------------------------------------------------------
+    for (int p = 0; p < nvalid; ++p) {
+        const long pp = pp0 + p;
+        const int n = static_cast<int>(static_cast<unsigned long>(pp) % static_cast<unsigned>(npx));
+        const int y = n / a.w, x = n - y * a.w;
+        if (lane < 4) a.corr16[pp * 328 + 324 + lane] = __float2half_rn(0.0f);
+        const float* cbase = a.coords1 + (pp - n) * 2;
+        __half* fp = a.flowpatch16 + pp * 104 + lane;
+        const int ch = lane & 1;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (k < 3 || lane < kLkWin * kLkWin - 96) {
-                const unsigned gx = static_cast<unsigned>(X0 + t.ex[k]), gy = static_cast<unsigned>(Y0 + t.ey[k]);
-                const bool inside = gx < static_cast<unsigned>(wl) && gy < static_cast<unsigned>(hl);
-                const unsigned off = inside ? gy * static_cast<unsigned>(wl) + gx : 0u;
-                const float v = __half2float(__ldg(base + off));
-                win[l * kLkLevelFloats + lane + 32 * k] = inside ? v : 0.0f;
+            if (k < 3 || lane < 104 - 96) {
+                const unsigned xx = static_cast<unsigned>(x + t.fdx[k]), yy = static_cast<unsigned>(y + t.fdy[k]);
+                const bool inside = (k < 3 || lane < 98 - 96) && xx < static_cast<unsigned>(a.w) && yy < static_cast<unsigned>(a.h);
+                const unsigned off = inside ? (yy * static_cast<unsigned>(a.w) + xx) * 2u + static_cast<unsigned>(ch) : 0u;
+                float v = __ldcg(cbase + off) - static_cast<float>(ch == 0 ? xx : yy);
+                v = inside ? v : 0.0f;
+                fp[32 * k] = __float2half_rn(v);
             }
         }
-        hl >>= 1; wl >>= 1;
-    }
-}
-
-// Phase 2 (after a __syncwarp): blend, write corr16 [324 + 4 pad], the 7x7x2 flow neighbourhood for convf1 and the flow
-// channels of the GRU record.
-// (x, y) = the pixel's position in its frame (pp = pair * h*w + y*w + x).
-__device__ __forceinline__ void lookup_emit(const LookupArgs& a, const LookupLane& t, long pp, int x, int y, int lane,
-                                            const float* win, const LookupPixel& px) {
-    const int n = y * a.w + x;
-    __half* out = a.corr16 + pp * 328 + lane;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const float* W = win + l * kLkLevelFloats;
-        const float wE = px.wE[l], wS = px.wS[l];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (k < 2 || lane < 81 - 64) {
-                const float* q = W + t.woff[k];
-                const float vnw = q[0], vne = q[1], vsw = q[kLkWin], vse = q[kLkWin + 1];
-                const float top = fmaf(wE, vne - vnw, vnw), bot = fmaf(wE, vse - vsw, vsw);
-                const float r = px.finite ? fmaf(wS, bot - top, top) : NAN;
-                out[l * 81 + 32 * k] = __float2half_rn(r);
-            }
+        if (lane < 2) {
+            const float cc = __ldcg(a.coords1 + pp * 2 + lane);
+            a.X[pp * 512 + 382 + lane] = __float2half_rn(cc - static_cast<float>(lane == 0 ? x : y));
         }
     }
-    if (lane < 4) out[324] = __float2half_rn(0.0f);
-    // flow = coords1 - coords0 (core/raft.py:179); 7x7x2 zero-padded neighbourhood for convf1
-    const float* cbase = a.coords1 + (pp - n) * 2;
-    __half* fp = a.flowpatch16 + pp * 104 + lane;
-    const int ch = lane & 1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < 3 || lane < 104 - 96) {
-            const unsigned xx = static_cast<unsigned>(x + t.fdx[k]), yy = static_cast<unsigned>(y + t.fdy[k]);
-            const bool inside = (k < 3 || lane < 98 - 96) && xx < static_cast<unsigned>(a.w) && yy < static_cast<unsigned>(a.h);
-            const unsigned off = inside ? (yy * static_cast<unsigned>(a.w) + xx) * 2u + static_cast<unsigned>(ch) : 0u;
-            float v = __ldcg(cbase + off) - static_cast<float>(ch == 0 ? xx : yy);
-            v = inside ? v : 0.0f;
-            fp[32 * k] = __float2half_rn(v);
-        }
-    }
-    if (lane < 2) a.X[pp * 512 + 382 + lane] = __float2half_rn((lane == 0 ? px.cx : px.cy) - static_cast<float>(lane == 0 ? x : y));
 }
 
 }  // namespace mftb

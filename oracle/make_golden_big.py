@@ -10,8 +10,10 @@ Run in the build container (needs /root/reference):   python -m oracle.make_gold
                                     frames 33/34 are steady-state frames (7 live chains) of the benchmarked workload
   tests/golden/raft_1024_32it.npz   BASELINE config 4's pair shape: one 1024x1024 pair (synthetic frames 0 -> 8), 32 iterations,
                                     through the reference's compute_flow (MFT/raft.py:39-73, core/raft.py:97-259)
-  oracle/_ref/frames_*.npy          the uint8 input frames (git-ignored, travel to the GPU box with the checkpoint); the
-                                    golden files hold their CRC32s
+  The golden files hold the CRC32 of every input frame.  The frames are regenerated at test time (synthetic video: the
+  seeded generator; demo video: decoded from the copy in oracle/_ref/, data like the checkpoint) and must reproduce the
+  CRCs -- they did on the B200 boxes (same image, same cv2).  GOLDEN_SAVE_FRAMES=1 also writes oracle/_ref/frames_*.npy
+  (git-ignored, travels to the GPU box) as a fallback for boxes where they would not.
 
 The best-chain index is not returned by the reference (MFT.py:123-124 keeps it local).  It is recomputed here from the
 reference's OWN per-delta flows (recorded at its flower) and its OWN stored left results with the reference's chain_results and
@@ -115,7 +117,8 @@ def track_run(model, frames, keep, name):
         print(f'{name}: frame {i} ({len(live)} chains) {time.time() - t0:.1f}s', flush=True)
     g['stats'] = np.stack(stats)
     np.savez_compressed(os.path.join(OUT, f'track_{name}.npz'), **g)
-    np.save(os.path.join(REFDATA, f'frames_{name}.npy'), np.stack(frames))
+    if os.environ.get('GOLDEN_SAVE_FRAMES'):          # only needed if the frames cannot be regenerated bit for bit on the GPU box
+        np.save(os.path.join(REFDATA, f'frames_{name}.npy'), np.stack(frames))
 
 
 def main():
@@ -136,7 +139,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, 'raft_1024_32it.npz'), result=np.ascontiguousarray(full[:, ::2, ::2]),
                             coords=_np(ex['raw']['coords'][0]), stats=field_stats(full), quantiles=np.array(QS),
                             frame_crc=np.array([crc(f) for f in pair], np.uint32), iters=np.array(32))
-        np.save(os.path.join(REFDATA, 'frames_1024.npy'), np.stack(pair))
+        if os.environ.get('GOLDEN_SAVE_FRAMES'):
+            np.save(os.path.join(REFDATA, 'frames_1024.npy'), np.stack(pair))
         print(f'1024x1024 / 32 iterations: {time.time() - t0:.1f}s', flush=True)
     if what in ('synth', 'all'):
         track_run(real, list(synthetic_video(35, 512, 512, seed=1234)), (1, 8, 33, 34), 'synth_512')

@@ -89,8 +89,10 @@ def _run_tracking(weights, g, frames, tag):
 
 
 def test_track_demo_512_40_frames_vs_reference(real_weights):
+    from oracle import fetch_ref_assets
     g = golden('track_demo_512.npz')
-    frames, src = frames_for(g, 'demo_512')
+    frames, src = frames_for(g, 'demo_512', regenerate=lambda: fetch_ref_assets.demo_frames(len(g['frame_crc']), size=(512, 512)))
+    record_parity('demo512_frames', {'source': src})
     _run_tracking(real_weights, g, frames, 'demo512')
 
 
