@@ -369,6 +369,10 @@ def run_ours(args):
     H, W = parse_size(args.size, 512)
     K, Wm = args.steps, args.warmup
     weights, wsrc = load_weights()
+    for kv in filter(None, os.environ.get('BENCH_GLOBAL_OPTIONS', '').split(',')):      # A/B runs of configure-time knobs, e.g. prog_split_n=1
+        from mft_b200 import engine as _E
+        k, v = kv.split('=')
+        _E.set_global_option(k.strip(), int(v))
     tracker = make_tracker(weights)
     n_frames = 1 + STEADY + 4 * (Wm + K) + 6              # room for one repeated measurement
     frames = list(synthetic_video(n_frames, H, W, seed=1234 + rank))

@@ -115,7 +115,7 @@ void conv_set_smem_cap_kib(int kib);
 // Persistent layer program: several dependent convolutions of the SAME spatial geometry executed by ONE launch of
 // resident CTAs with tile-level dataflow between layers (conv_prog_kernel in conv_tc.cu).
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxProgLayers = 12;
+constexpr int kMaxProgLayers = 16;
 
 struct ProgLayer {
     CUtensorMap tmA, tmB;

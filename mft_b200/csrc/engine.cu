@@ -42,6 +42,7 @@ struct Act {           // NHWC fp16 view
 };
 
 thread_local std::string g_create_error;
+int g_prog_split_n = 0;      // 1: the N = 256 layers of the iteration program (convc1, z|r, flow head 1) run as two 128-column slices
 
 inline const char* cu_err(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
 
@@ -388,8 +389,9 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     // the correlation branch (caller's stream) and the flow branch (side stream) are independent until `conv`
     // plan indices of the iteration's convolutions in program order, with their predecessor layers (conv_prog_kernel)
     int pi[11];
+    const int nt256 = g_prog_split_n ? 128 : 256;      // column slice of the 256-wide layers (two items per tile when split)
     S.push_back(sync_step(1));
-    S.push_back(B.step(pi[0] = B.conv16(L_CONVC1, a_corr, mp, 1, t1, 256, 1, c->c1buf, 256, 0, 256), true));
+    S.push_back(B.step(pi[0] = B.conv16(L_CONVC1, a_corr, mp, 1, t1, nt256, 1, c->c1buf, 256, 0, 256), true));
     S.push_back(B.step(pi[1] = B.conv16(L_CONVF1, a_fp, mp, 1, t1, 128, 1, c->f1buf, 128, 0, 128), true));
     S.back().lane = 1;
     S.push_back(B.step(pi[2] = B.conv16(L_CONVC2, a_c1, mp, 1, t3, 192, 1, c->cf, 256, 0, 192), true));
@@ -400,7 +402,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     // SepConvGRU (update.py:108-123): horizontal 1x5 then vertical 5x1
     for (int pass = 0; pass < 2; ++pass) {
         const TapList& tp = pass == 0 ? t15 : t51;
-        const int izr = B.conv(pass == 0 ? L_GRU_ZR1 : L_GRU_ZR2, a_hx, mp, 1, tp, 256, EPI_GRU_ZR);
+        const int izr = B.conv(pass == 0 ? L_GRU_ZR1 : L_GRU_ZR2, a_hx, mp, 1, tp, nt256, EPI_GRU_ZR);
         if (izr >= 0) {
             ConvEpi& e = B.epi(izr);
             e.n_valid = 256; e.z32 = c->z32; e.h32 = c->h32; e.out16 = c->X; e.out16_stride = 512; e.out16_coff = 384;
@@ -416,7 +418,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         pi[6 + 2 * pass] = iq;
     }
     // flow head (update.py:6-14) ; coords1 += delta_flow (core/raft.py:184)
-    S.push_back(B.step(pi[9] = B.conv16(L_FH1, a_h, mp, 1, t3, 256, 1, c->fhbuf, 256, 0, 256), true));
+    S.push_back(B.step(pi[9] = B.conv16(L_FH1, a_h, mp, 1, t3, nt256, 1, c->fhbuf, 256, 0, 256), true));
     {
         const int i = B.conv(L_FH2, a_fh, mp, 1, t3, 16, EPI_FLOW);
         if (i >= 0) {
@@ -452,14 +454,36 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             return hq != nullptr && P.queue != nullptr && P.arrivals != nullptr;
         };
         c->prog_timing = c->dalloc<long long>(8 * 1024);
+        // A logical layer becomes one program layer per output-column slice of its plan (n_tiles); a successor depends on
+        // every slice of its predecessors (at most two program layers in all: checked).
+        auto build = [&](ConvProgram& P, const int (*deps)[2], int first_id, bool exact_halo) -> const char* {
+            std::vector<std::vector<int>> ids(11);
+            for (int k = 0; k < 11; ++k) {
+                int d[2] = {-1, -1}, nd = 0;
+                for (int j = 0; j < 2; ++j) {
+                    const int dk = deps[k][j];
+                    if (dk < 0) continue;
+                    if (dk < first_id) { if (nd == 2) return "program: more than two dependencies"; d[nd++] = dk; continue; }   // the lookup layer
+                    for (int id : ids[dk - first_id]) { if (nd == 2) return "program: more than two dependencies"; d[nd++] = id; }
+                }
+                const int slices = c->plans[pi[k]].g.n_tiles;
+                for (int ny = 0; ny < slices; ++ny) {
+                    if (const char* e = conv_prog_add(&P, c->plans[pi[k]], d[0], d[1], exact_halo, ny)) return e;
+                    ids[k].push_back(P.n_layers - 1);
+                }
+            }
+            return nullptr;
+        };
         memset(&c->prog, 0, sizeof c->prog);
-        const char* pe = nullptr;
-        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog, c->plans[pi[k]], depsA[k][0], depsA[k][1], true);
+        const char* pe = build(c->prog, depsA, 0, true);
         if (!pe) c->prog_ok = finish(c->prog, 1);
         memset(&c->prog_full, 0, sizeof c->prog_full);
         LookupArgs lk{{c->corr[0], c->corr[1], c->corr[2], c->corr[3]}, c->coords1, c->corr16, c->flowpatch, c->X, mp, h, w};
-        pe = conv_prog_add_lookup(&c->prog_full, c->plans[pi[0]], lk, 11);
-        for (int k = 0; k < 11 && !pe; ++k) pe = conv_prog_add(&c->prog_full, c->plans[pi[k]], depsB[k][0], depsB[k][1], false);
+        // the lookup (layer 0) consumes the PREVIOUS iteration's flow head 2 = the last program layer
+        int n_conv_layers = 0;
+        for (int k = 0; k < 11; ++k) n_conv_layers += c->plans[pi[k]].g.n_tiles;
+        pe = conv_prog_add_lookup(&c->prog_full, c->plans[pi[0]], lk, n_conv_layers);
+        if (!pe) pe = build(c->prog_full, depsB, 1, false);
         if (!pe) c->prog_full_ok = finish(c->prog_full, 64);
     }
 
@@ -1090,6 +1114,7 @@ int mftb200_set_global_option(const char* key, int value) {
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }
     if (strcmp(key, "smem_cap_kib") == 0) { conv_set_smem_cap_kib(value); return MFTB200_OK; }
+    if (strcmp(key, "prog_split_n") == 0) { g_prog_split_n = value ? 1 : 0; return MFTB200_OK; }      // next configure()
     return MFTB200_ERR_ARG;
 }
 

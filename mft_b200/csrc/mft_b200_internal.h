@@ -16,7 +16,8 @@ extern "C" {
  * conv-kernel knobs read by the next mftb200_configure. */
 
 /* Process-wide conv-kernel tuning knobs (read when plans are built): "conv_v2" bit0 = use the 256-pixel haloed
- * kernel, bit1 = descriptor base-offset mode; "pdl"; "cluster"; "smem_cap_kib". */
+ * kernel, bit1 = descriptor base-offset mode; "pdl"; "cluster"; "smem_cap_kib"; "prog_split_n" 0|1 = the 256-column
+ * layers of the iteration program as two 128-column slices (twice the work items, half the per-item latency). */
 int mftb200_set_global_option(const char* key, int value);
 /* Named internal buffer for stage-level parity tests ("fmap_slots", "net_slots", "corr_l0", ...). */
 int mftb200_debug_buffer(mftb200_ctx* ctx, const char* name, void** ptr, size_t* bytes);

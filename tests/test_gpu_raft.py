@@ -246,6 +246,37 @@ def test_persistent_program_bit_identical(geom, seeded_weights):
             assert torch.equal(ref1, got1), (geom, mode, rep)
 
 
+def test_program_column_split_bit_identical(seeded_weights):
+    """Global option prog_split_n: the 256-column layers of the iteration program (convc1, z|r, flow head 1) as two
+    128-column work items per tile.  An output column's K order does not depend on the column tiling, so not a single bit
+    may change -- in the per-layer path, the per-iteration program and the all-iterations program."""
+    from mft_b200 import engine as E
+    from mft_b200.synth import synthetic_video
+    H, Wd, pairs = 256, 256, 5
+    frames = list(synthetic_video(pairs + 1, H, Wd, seed=23))
+    lefts, rights = list(range(pairs)), [pairs] * pairs
+    res = {}
+    try:
+        for split in (0, 1):
+            E.set_global_option('prog_split_n', split)
+            eng = _engine(seeded_weights, H, Wd, pairs=pairs, slots=pairs + 1)
+            for i, f in enumerate(frames):
+                eng.encode_frame(f, i)
+            for mode in (0, 1, 2):
+                eng.set_option('persist', mode)
+                res[(split, mode)] = eng.refine(lefts, rights).clone()
+                eng.check_device()
+            del eng
+    finally:
+        E.set_global_option('prog_split_n', 0)
+    ref = res[(0, 0)]
+    # (two encodes of a frame differ in the last bits of the instance-norm statistics: compare within one engine, and the
+    # two engines' per-layer results against each other with a tolerance)
+    for mode in (1, 2):
+        assert torch.equal(res[(0, mode)], res[(0, 0)]) and torch.equal(res[(1, mode)], res[(1, 0)]), mode
+    assert float((res[(1, 0)][:, :2] - ref[:, :2]).abs().max()) < 0.05
+
+
 def test_tracker_vs_oracle_real_128(real_weights):
     """mft_b200.MFT.MFT against the oracle tracker and the reference tracker's golden results."""
     from mft_b200.config import Config
