@@ -597,7 +597,7 @@ cudaError_t launch_ou_pack(const OuPackArgs& a, cudaStream_t stream) {
 // ==========================================================================================
 // convex 8x upsampling of flow / occlusion logits / uncertainty with one shared mask
 // (core/raft.py:83-94,190-218) + post-processing and unpadding (MFT/raft.py:56-62)
-// 64 threads per coarse pixel (one per 8x8 sub-position), 4 coarse pixels per block
+// 64 threads per coarse pixel (one per 8x8 sub-position), 4 consecutive coarse pixels per block
 // ==========================================================================================
 __global__ void __launch_bounds__(256)
 upsample_kernel(const UpsampleArgs a) {
@@ -628,11 +628,14 @@ upsample_kernel(const UpsampleArgs a) {
         for (int j = 0; j < 5; ++j) nb[qd][k][j] = v[j];
     }
     __syncthreads();
-    const int qd = threadIdx.x >> 6;
+    // thread -> (sub-row sy = warp, coarse pixel qd, sub-column sx): a warp writes ONE full-resolution row segment of the
+    // block's 4 consecutive coarse pixels = 32 consecutive floats per plane (128-byte stores; round 1 had a warp cover
+    // 4 rows x 8 columns = 32-byte runs) and reads four 32-byte runs of the mask per neighbour
+    const int qd = (threadIdx.x >> 3) & 3;
     const long pp = static_cast<long>(blockIdx.x) * 4 + qd;
     if (pp >= total) return;
-    const int sub = threadIdx.x & 63;
-    const int sy = sub >> 3, sx = sub & 7;
+    const int sy = threadIdx.x >> 5, sx = threadIdx.x & 7;
+    const int sub = sy * 8 + sx;
     const int pair = static_cast<int>(static_cast<unsigned>(pp) / static_cast<unsigned>(npx)), n = static_cast<int>(pp) - pair * npx;
     const int y = n / a.w, x = n - y * a.w;
     const float* m = a.mask32 + pp * 576 + sub;
