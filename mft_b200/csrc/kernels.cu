@@ -534,22 +534,35 @@ cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L
 // The routine lives in lookup.cuh (shared with the persistent refinement kernel, which can run the same lookup as tiles
 // of its dataflow program).  Here: one warp per group of kLkGroup consecutive (pair, source pixel)s, 8 groups per block.
 __global__ void __launch_bounds__(256, 5)
-lookup_kernel(const LookupArgs a) {
+lookup_kernel(const LookupArgs a, const long n_groups) {
     pdl_enter();
     __shared__ __align__(16) float win[8][kLkWinFloats];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    const long pp0 = (static_cast<long>(blockIdx.x) * 8 + wib) * kLkGroup;
-    if (pp0 >= total) return;
     const LookupLane t = lookup_lane_init(lane);
-    const long left = total - pp0;
-    lookup_group(a, t, pp0, left < kLkGroup ? static_cast<int>(left) : kLkGroup, lane, win[wib]);
+    // grid-stride over the groups: the grid is one resident wave, so there is no tail wave of a few blocks
+    {
+        const long g = static_cast<long>(blockIdx.x) * 8 + wib;
+        if (g >= n_groups) return;
+        const long pp0 = g * kLkGroup;
+        const long left = total - pp0;
+        lookup_group(a, t, pp0, left < kLkGroup ? static_cast<int>(left) : kLkGroup, lane, win[wib]);
+        __syncwarp();
+    }
 }
 
 cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream) {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
-    const long per_block = 8 * kLkGroup;
-    return launch_pdl(lookup_kernel, dim3(static_cast<unsigned>((total + per_block - 1) / per_block)), dim3(256), 0, stream, a);
+    const long n_groups = (total + kLkGroup - 1) / kLkGroup;
+    long blocks = (n_groups + 7) / 8;
+    if (blocks > static_cast<long>(n_sm) * 5) blocks = static_cast<long>(n_sm) * 5;       // 5 resident blocks per SM (launch bounds)
+    return launch_pdl(lookup_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a, n_groups);
 }
 
 // ==========================================================================================

@@ -13,7 +13,7 @@
 // bound (808 warp instructions per pixel, 35 us per iteration at 512^2).  Now, level by level for the whole group:
 //   gather   lane task = (pixel, window row, aligned chunk of VEC = 4 | 2 | 1 fp16 elements): 8-byte loads where the
 //            level's width allows it; a chunk lies either wholly inside the map or wholly outside (zero), so there is
-//            no per-element bounds handling; the chunk lands in shared memory as fp32 [pixel][row][16];
+//            no per-element bounds handling; the chunk lands in shared memory as fp32 [pixel][row][16 | 12 | 10];
 //   blend    lane task = (pixel, output column i): separable -- 10 horizontal lerps H[row] = lerp(W[row][i], W[row][i+1])
 //            down the column, 9 vertical lerps between consecutive rows (171 lerps per pixel and level instead of 243,
 //            2 shared-memory reads per row instead of 4 per output), the column's 9 outputs are consecutive channels
@@ -26,8 +26,7 @@
 namespace mftb {
 
 constexpr int kLkGroup = 4;                              // pixels per warp pass
-constexpr int kLkRowFloats = 16;                         // shared-memory floats per window row (aligned span of the 10 taps)
-constexpr int kLkWinFloats = kLkGroup * 10 * kLkRowFloats;   // one level's windows of a group: 2560 bytes per warp
+constexpr int kLkWinFloats = kLkGroup * 10 * 16;         // one level's windows of a group: at most 2560 bytes per warp
 
 // Per-lane constants of the 7x7x2 flow patch: entry f = lane + 32k (k < 4, f < 98): channel f & 1 of tap (f >> 1) = ky * 7 + kx.
 struct LookupLane {
@@ -56,10 +55,13 @@ __device__ __forceinline__ float lk_roundtrip_div(float c, float size_m1) {
     return ((g + 1.0f) * 0.5f) * size_m1;
 }
 
-// Loads of one level for the group: up to kRounds chunks per lane, kept in registers until lookup_store_level.
+// Geometry of one level's gather for vector width VEC: a window row is covered by kPerRow aligned chunks of VEC elements;
+// task T = (pixel p, row, chunk) = ((p * 10 + row) * kPerRow + chunk) lands at float T * VEC of the window buffer, i.e.
+// the buffer is [pixel][row][kPitch = kPerRow * VEC] and needs no address arithmetic on the store side.
 template <int VEC>
 struct LkChunks {
-    static constexpr int kPerRow = VEC == 4 ? 4 : (VEC == 2 ? 6 : 10);          // aligned chunks covering the 10 taps of a row
+    static constexpr int kPerRow = VEC == 4 ? 4 : (VEC == 2 ? 6 : 10);
+    static constexpr int kPitch = kPerRow * VEC;                                // 16 | 12 | 10 floats per window row
     static constexpr int kTasks = kLkGroup * 10 * kPerRow;
     static constexpr int kRounds = (kTasks + 31) / 32;
     static constexpr int kWords = VEC == 4 ? 2 : 1;                             // 32-bit registers per chunk
@@ -69,12 +71,12 @@ struct LkRegs {
     unsigned w[13];
 };
 
-// Issues the loads of level `l`.  lane (p * 4 + l) holds X0 / Y0 of (pixel p, level l).
+// Issues the loads of level `l`.  lane (p * 4 + l) holds X0 / Y0 of (pixel p, level l); base0 = the level's image of pixel pp0.
 template <int VEC>
-__device__ __forceinline__ void lookup_load_level(const __half* __restrict__ lvl, int hl, int wl, long pp0, unsigned valid_mask, int l,
+__device__ __forceinline__ void lookup_load_level(const __half* __restrict__ base0, int hl, int wl, unsigned valid_mask, int l,
                                                   int myX0, int myY0, int lane, LkRegs& c) {
     using C = LkChunks<VEC>;
-    const long img = static_cast<long>(hl) * wl;
+    const int img = hl * wl;                                                    // (4 images: 32-bit offsets)
 #pragma unroll
     for (int r = 0; r < C::kRounds; ++r) {
         const int T = r * 32 + lane;
@@ -89,7 +91,7 @@ __device__ __forceinline__ void lookup_load_level(const __half* __restrict__ lvl
                             static_cast<unsigned>(gy) < static_cast<unsigned>(hl);
         uint2 v = make_uint2(0u, 0u);
         if (inside) {
-            const __half* q = lvl + (pp0 + p) * img + (gy * wl + gx);
+            const __half* q = base0 + (p * img + gy * wl + gx);
             if constexpr (VEC == 4) v = __ldg(reinterpret_cast<const uint2*>(q));
             else if constexpr (VEC == 2) v.x = __ldg(reinterpret_cast<const unsigned*>(q));
             else v.x = __ldg(reinterpret_cast<const unsigned short*>(q));
@@ -99,7 +101,7 @@ __device__ __forceinline__ void lookup_load_level(const __half* __restrict__ lvl
     }
 }
 
-// Converts the chunks to fp32 and stores them into the group's window buffer [pixel][row][16].
+// Converts the chunks to fp32 and stores them into the group's window buffer [pixel][row][kPitch].
 template <int VEC>
 __device__ __forceinline__ void lookup_store_level(const LkRegs& c, int lane, float* win) {
     using C = LkChunks<VEC>;
@@ -107,10 +109,7 @@ __device__ __forceinline__ void lookup_store_level(const LkRegs& c, int lane, fl
     for (int r = 0; r < C::kRounds; ++r) {
         const int T = r * 32 + lane;
         if (T < C::kTasks) {
-            const int p = T / (10 * C::kPerRow);
-            const int t = T - p * (10 * C::kPerRow);
-            const int row = t / C::kPerRow, ch = t - row * C::kPerRow;
-            float* dst = win + (p * 10 + row) * kLkRowFloats + ch * VEC;
+            float* dst = win + T * VEC;
             if constexpr (VEC == 4) {
                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[2 * r]));
                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[2 * r + 1]));
@@ -126,46 +125,66 @@ __device__ __forceinline__ void lookup_store_level(const LkRegs& c, int lane, fl
     }
 }
 
-// Blends level `l` of the group out of `win` and writes channels [81 l, 81 l + 81) of corr16.
+// channels 81 l + 9 i + (j0 ..): n consecutive halves at a 2-byte aligned offset -> 4-byte words plus a leading / trailing half
+__device__ __forceinline__ void lk_store9(__half* dst, const float (&o)[9], bool word_aligned) {
+    if (word_aligned) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<__half2*>(dst + 2 * k) = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+        dst[8] = __float2half_rn(o[8]);
+    } else {
+        dst[0] = __float2half_rn(o[0]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<__half2*>(dst + 1 + 2 * k) = __floats2half2_rn(o[1 + 2 * k], o[2 + 2 * k]);
+    }
+}
+
+// Blends level `l` of the group out of `win` (row pitch `pitch` floats) and writes channels [81 l, 81 l + 81) of corr16.
 // lane (p * 4 + l) holds wE / wS / the window's column offset within its aligned span / finiteness of (pixel p, level l).
+// Round A: lane = (pixel p, output column i < 8): the whole column, 10 horizontal + 9 vertical lerps.  Round B: the ninth
+// column of the four pixels, one output per lane (36 outputs: lanes 0..31, then lanes 0..3) -- a second column round would
+// keep 4 of 32 lanes busy.
+template <int VEC>
 __device__ __forceinline__ void lookup_blend_level(__half* __restrict__ corr16, long pp0, unsigned valid_mask, int l, float my_wE, float my_wS,
                                                    int my_off, int my_finite, int lane, const float* win) {
+    constexpr int pitch = LkChunks<VEC>::kPitch;
+    {
+        const int p = lane >> 3, i = lane & 7;
+        const int src = p * 4 + l;
+        const float wE = __shfl_sync(0xffffffffu, my_wE, src), wS = __shfl_sync(0xffffffffu, my_wS, src);
+        const int off = __shfl_sync(0xffffffffu, my_off, src), fin = __shfl_sync(0xffffffffu, my_finite, src);
+        if ((valid_mask >> p) & 1u) {
+            const float* q = win + p * 10 * pitch + off + i;
+            float o[9];
+            float prev = 0.0f;
 #pragma unroll
-    for (int r = 0; r < (kLkGroup * 9 + 31) / 32; ++r) {
-        const int T = r * 32 + lane;
-        int p = (T * 57) >> 9;                               // T / 9 (T < 64)
-        const int i = T - p * 9;
-        const bool active = T < kLkGroup * 9 && ((valid_mask >> (p < kLkGroup ? p : 0)) & 1u);
+            for (int row = 0; row < 10; ++row) {
+                const float vw = q[row * pitch], ve = q[row * pitch + 1];
+                const float h = fmaf(wE, ve - vw, vw);
+                if (row > 0) o[row - 1] = fin ? fmaf(wS, h - prev, prev) : NAN;
+                prev = h;
+            }
+            lk_store9(corr16 + (pp0 + p) * 328 + (l * 81 + i * 9), o, ((l + i) & 1) == 0);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int T = r * 32 + lane;                      // (pixel p, output row j) of column 8
+        int p = (T * 57) >> 9;                            // T / 9 (T < 64)
+        const int j = T - p * 9;
+        const bool active = T < kLkGroup * 9;
         p = p < kLkGroup ? p : kLkGroup - 1;
         const int src = p * 4 + l;
         const float wE = __shfl_sync(0xffffffffu, my_wE, src), wS = __shfl_sync(0xffffffffu, my_wS, src);
         const int off = __shfl_sync(0xffffffffu, my_off, src), fin = __shfl_sync(0xffffffffu, my_finite, src);
-        if (!active) continue;
-        const float* q = win + p * 10 * kLkRowFloats + off + i;
-        float o[9];
-        float prev = 0.0f;
-#pragma unroll
-        for (int row = 0; row < 10; ++row) {
-            const float vw = q[row * kLkRowFloats], ve = q[row * kLkRowFloats + 1];
-            const float h = fmaf(wE, ve - vw, vw);
-            if (row > 0) o[row - 1] = fin ? fmaf(wS, h - prev, prev) : NAN;
-            prev = h;
-        }
-        // channels 81 l + 9 i + (0..8): 18 bytes at a 2-byte aligned offset -> 4-byte words plus one leading / trailing half
-        __half* dst = corr16 + (pp0 + p) * 328 + (l * 81 + i * 9);
-        if (((l + i) & 1) == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<__half2*>(dst + 2 * k) = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
-            dst[8] = __float2half_rn(o[8]);
-        } else {
-            dst[0] = __float2half_rn(o[0]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<__half2*>(dst + 1 + 2 * k) = __floats2half2_rn(o[1 + 2 * k], o[2 + 2 * k]);
+        if (active && ((valid_mask >> p) & 1u)) {
+            const float* q = win + (p * 10 + j) * pitch + off + 8;
+            const float top = fmaf(wE, q[1] - q[0], q[0]), bot = fmaf(wE, q[pitch + 1] - q[pitch], q[pitch]);
+            const float v = fin ? fmaf(wS, bot - top, top) : NAN;
+            corr16[(pp0 + p) * 328 + (l * 81 + 72 + j)] = __float2half_rn(v);
         }
     }
 }
 
-// One level: store its chunks, (issue the next level's loads by the caller), blend.  Dispatch on the level's vector width.
 __device__ __forceinline__ int lookup_vec(int wl) { return (wl & 3) == 0 ? 4 : ((wl & 1) == 0 ? 2 : 1); }
 
 // The whole lookup of pixels pp0 .. pp0 + nvalid - 1 (global pixel indices pair * h*w + n; nvalid <= kLkGroup) by one warp.
@@ -197,25 +216,27 @@ __device__ __forceinline__ void lookup_group(const LookupArgs& a, const LookupLa
     LkRegs regs;
     auto load = [&](int l) {
         const int hl = a.h >> l, wl = a.w >> l;
+        // (no dynamic indexing of the kernel parameter: that would force a local-memory copy of the whole struct)
+        const __half* lv = l == 0 ? a.lvl[0] : (l == 1 ? a.lvl[1] : (l == 2 ? a.lvl[2] : a.lvl[3]));
+        const __half* base0 = lv + pp0 * (static_cast<long>(hl) * wl);
         const int v = lookup_vec(wl);
-        if (v == 4) lookup_load_level<4>(a.lvl[l], hl, wl, pp0, valid_mask, l, my_X0, my_Y0, lane, regs);
-        else if (v == 2) lookup_load_level<2>(a.lvl[l], hl, wl, pp0, valid_mask, l, my_X0, my_Y0, lane, regs);
-        else lookup_load_level<1>(a.lvl[l], hl, wl, pp0, valid_mask, l, my_X0, my_Y0, lane, regs);
-    };
-    auto store = [&](int l) {
-        const int v = lookup_vec(a.w >> l);
-        if (v == 4) lookup_store_level<4>(regs, lane, win);
-        else if (v == 2) lookup_store_level<2>(regs, lane, win);
-        else lookup_store_level<1>(regs, lane, win);
+        if (v == 4) lookup_load_level<4>(base0, hl, wl, valid_mask, l, my_X0, my_Y0, lane, regs);
+        else if (v == 2) lookup_load_level<2>(base0, hl, wl, valid_mask, l, my_X0, my_Y0, lane, regs);
+        else lookup_load_level<1>(base0, hl, wl, valid_mask, l, my_X0, my_Y0, lane, regs);
     };
     load(0);
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
+        const int v = lookup_vec(a.w >> l);
         __syncwarp();                      // the previous level's blend is done with the buffer
-        store(l);
+        if (v == 4) lookup_store_level<4>(regs, lane, win);
+        else if (v == 2) lookup_store_level<2>(regs, lane, win);
+        else lookup_store_level<1>(regs, lane, win);
         if (l < 3) load(l + 1);
         __syncwarp();
-        lookup_blend_level(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
+        if (v == 4) lookup_blend_level<4>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
+        else if (v == 2) lookup_blend_level<2>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
+        else lookup_blend_level<1>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
     }
     // ---- per pixel: zero pad of corr16, the 7x7x2 zero-padded flow neighbourhood for convf1 (flow = coords1 - coords0,
     //      core/raft.py:179) and the flow channels of the GRU record ------------------------------------------------------------------

@@ -396,3 +396,53 @@ def test_roofline_flop_counts_follow_the_layer_shapes():
     assert abs(F - 2.09e12) < 0.01e12
     assert F == 2 * ((H // 2) * (W // 2) * enc2 + (H // 4) * (W // 4) * 620544 + n * (1130496 + 65536)) + \
         7 * (2 * n * n * 256 + 11 * n * per_iter + n * last + n * ou)
+
+
+def test_tapvid_runner_host_logic():
+    """mft_b200.tapvid mirrors run_MFT_tapvid.py:140-285: per start frame a forward (+ backward in 'strided' mode) init/track
+    sequence, every frame's result sampled at that start frame's queries.  Exercised with a stand-in tracker (no GPU)."""
+    from types import SimpleNamespace
+    from mft_b200 import tapvid as TV
+    from mft_b200.results import FlowOUTrackingResult
+
+    class FakeTracker:
+        def __init__(self):
+            self.log = []
+
+        def init(self, img, start_frame_i=0, time_direction=1, flow_cache=None):
+            self.t, self.dir, self.start = start_frame_i, time_direction, start_frame_i
+            self.log.append(('init', start_frame_i, time_direction, int(img[0, 0, 0])))
+            return SimpleNamespace(result=FlowOUTrackingResult.identity(img.shape[:2]))
+
+        def track(self, img, debug=False, device_result=False):
+            self.t += self.dir
+            self.log.append(('track', self.t, int(img[0, 0, 0])))
+            r = FlowOUTrackingResult.identity(img.shape[:2])
+            r.flow[0] += float(self.t - self.start)           # x flow = signed frame distance from the start frame
+            return SimpleNamespace(result=r)
+
+    data = TV.synthetic_dataset(1, 12, 6, 32, seed=3)
+    d = data['synth-000']
+    assert d['video'].shape == (12, 32, 32, 3) and d['video'].dtype == np.uint8
+    assert d['points'].shape == (6, 12, 2) and d['occluded'].shape == (6, 12) and d['occluded'].dtype == np.bool_
+    assert float(d['points'].min()) >= 0 and float(d['points'].max()) <= 1
+    video = np.stack([np.full((32, 32, 3), i, np.uint8) for i in range(12)])          # frame i is filled with i
+    pts = d['points'] * 32
+    qf, qs = TV.sample_queries_first(d['occluded'], pts), TV.sample_queries_strided(d['occluded'], pts)
+    assert qf.shape[1] == 3 and all(not d['occluded'][i, int(q[0])] for i, q in enumerate(qf))
+    assert set(np.unique(qs[:, 0]).astype(int)) <= {0, 5, 10}
+    trk = FakeTracker()
+    tracks, occl, n = TV.run_sequence(trk, video, qs, 'strided', device='cpu')
+    starts = sorted(set(qs[:, 0].astype(int)))
+    assert n == sum((12 - s) + (s + 1) for s in starts)
+    inits = [e for e in trk.log if e[0] == 'init']
+    assert [(e[1], e[2]) for e in inits] == [(s, dirn) for s in starts for dirn in (1, -1)]
+    assert all(e[3] == e[1] for e in inits) and all(e[2] == e[1] for e in trk.log if e[0] == 'track')     # frame i went to time i
+    # a query started at frame s sits at x + (t - s) in frame t (the stand-in's flow), on both sides of s
+    q = qs.astype(np.int64)
+    for k in range(len(q)):
+        s, y, x = q[k]
+        for t in range(12):
+            assert abs(tracks[k, t, 0] - (x + (t - s))) < 1e-4 and abs(tracks[k, t, 1] - y) < 1e-4
+    tracks_f, _, n_f = TV.run_sequence(FakeTracker(), video, qf, 'first', device='cpu')
+    assert n_f == sum(12 - s for s in sorted(set(qf[:, 0].astype(int))))

@@ -135,7 +135,7 @@ def test_reference_config_path_and_demo_sequence(tmp_path, monkeypatch):
             got = result.packed().numpy()
             epe = np.sqrt(((got[:2] - want[:2]) ** 2).sum(0))
             record_parity(f'dropin_track128_frame{i}', dict(epe_median=np.median(epe), epe_mean=epe.mean()))
-            assert np.median(epe) < 0.02, (i, np.median(epe))
+            assert np.median(epe) < 0.0035, (i, np.median(epe))          # measured <= 0.0012 px
             # the point tracks are bilinear samples of that field (MFT/point_tracking.py:6-27)
             q = queries.cpu().numpy().astype(int)
             assert np.abs(coords - (q + got[:2, q[:, 1], q[:, 0]].T)).max() < 1e-4

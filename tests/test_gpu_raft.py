@@ -6,9 +6,7 @@ recurrent state, coordinates and outputs stay fp32.  The reference path is fp32,
 stated as a tolerance (north_star: "within a stated fp32 tolerance"):
 
     stage boundaries   max |err| <= 2 % of the tensor's max |value|   (fp16 rounding of operands)
-    flow (real weights) mean end-point error <= 0.05 px, 99.5 % of pixels within 0.5 px
-    occlusion          mean |err| <= 0.01
-    sigma              mean relative error <= 2 %
+    flow, occlusion, sigma: every gate is <= 3x the value measured on a B200 (profiles/r2_parity_measured.json), listed at the gate
 The same oracle run with bf16 operands gives mean EPE 0.004-0.015 px, max 0.12-0.69 px.
 """
 import numpy as np
@@ -96,8 +94,10 @@ def test_flow_real_128_vs_oracle_and_golden(real_weights):
         for ref in ((f, o, s), tuple(torch.from_numpy(g[f'{k}_{a}_{b}']) for k in ('flow', 'occ', 'sigma'))):
             st = _flow_stats(out[p], *ref)
             record_parity(f'real128_pair{a}_{b}_vs_' + ('oracle' if ref[0] is f else 'reference'), st)
-            assert st['epe_mean'] < 0.05 and st['epe_p995'] < 0.5, st
-            assert st['occ_mean'] < 0.01 and st['sigma_rel'] < 0.02, st
+            # measured (shipped checkpoint, 128x128): EPE mean 0.0007 / 0.0018 px (pairs 0->1 / 0->8), p99.5 0.006 / 0.025 px,
+            # occlusion <= 7e-5, sigma 0.08 %
+            assert st['epe_mean'] < 0.0055 and st['epe_p995'] < 0.075, st
+            assert st['occ_mean'] < 2.5e-4 and st['sigma_rel'] < 0.0025, st
 
 
 def test_config1_real_256(real_weights):
@@ -112,7 +112,8 @@ def test_config1_real_256(real_weights):
     got = torch.cat([flow, extra['occlusion'], extra['sigma']])
     st = _flow_stats(got, torch.from_numpy(g['flow_0_1']), torch.from_numpy(g['occ_0_1']), torch.from_numpy(g['sigma_0_1']))
     record_parity('config1_real256_vs_reference', st)
-    assert st['epe_mean'] < 0.05 and st['epe_p995'] < 0.5 and st['occ_mean'] < 0.01 and st['sigma_rel'] < 0.02, st
+    # measured: EPE mean 0.0006 px, p99.5 0.0041 px, occlusion 2e-5, sigma 0.09 %
+    assert st['epe_mean'] < 0.0018 and st['epe_p995'] < 0.0125 and st['occ_mean'] < 1e-4 and st['sigma_rel'] < 0.003, st
     src, dst, ex = fl.compute_flow(g['frames'][0], g['frames'][1], mode='TC')
     assert tuple(src.shape) == (2, 256 * 256) and torch.allclose(dst - src, flow.reshape(2, -1), atol=1e-4)
 
@@ -130,7 +131,8 @@ def test_padding_and_ragged_tiles_seeded(size, seeded_weights):
     f, o, s = O.compute_flow(seeded_weights, frames[0], frames[1])
     st = _flow_stats(out[0], f, o, s)
     record_parity(f'seeded_{H}x{Wd}_vs_oracle', st)
-    assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
+    # measured (seeded stand-in weights: rougher activations than the checkpoint's): EPE mean 0.039 / 0.043 px, occlusion 5e-4
+    assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.13 and st['epe_p995'] < 0.42 and st['occ_mean'] < 0.0015, st
 
 
 def test_padded_size_vs_reference_golden(seeded_weights):
@@ -143,7 +145,8 @@ def test_padded_size_vs_reference_golden(seeded_weights):
     eng.check_device()
     st = _flow_stats(out[0], torch.from_numpy(g['flow_0_2']), torch.from_numpy(g['occ_0_2']), torch.from_numpy(g['sigma_0_2']))
     record_parity('seeded_131x140_vs_reference', st)
-    assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.25 and st['occ_mean'] < 0.03, st
+    # measured: EPE mean 0.040 px, p99.5 0.133 px, occlusion 7e-4 (seeded weights)
+    assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.12 and st['epe_p995'] < 0.4 and st['occ_mean'] < 0.002, st
 
 
 @pytest.mark.parametrize('size', [(128, 160), (256, 256)])
@@ -303,12 +306,14 @@ def test_tracker_vs_oracle_real_128(real_weights):
                                                  index_agree=agree, mean_diff=np.abs(got.reshape(4, -1).mean(1) - g['means'][i - 1]).max()))
         # chains multiply small flow differences by selection flips at near-ties: judge the field
         # by robust statistics and the index map by agreement rate
-        assert np.median(epe) < 0.05 and np.quantile(epe, 0.95) < 0.5, (i, np.median(epe), np.quantile(epe, 0.95))
-        assert agree > 0.90, (i, agree)
-        assert np.abs(got.reshape(4, -1).mean(1) - g['means'][i - 1]).max() < 0.05
+        # measured over the 9 frames: EPE median <= 0.0012 px, p95 <= 0.0066 px, index agreement >= 0.9859, channel means
+        # within 6.4e-4 of the reference tracker's
+        assert np.median(epe) < 0.0035 and np.quantile(epe, 0.95) < 0.02, (i, np.median(epe), np.quantile(epe, 0.95))
+        assert agree > 0.958, (i, agree)
+        assert np.abs(got.reshape(4, -1).mean(1) - g['means'][i - 1]).max() < 0.002
         if f'result_{i}' in g.files:
             epe_ref = np.sqrt(((got[:2] - g[f'result_{i}'][:2]) ** 2).sum(0))
-            assert np.median(epe_ref) < 0.05
+            assert np.median(epe_ref) < 0.0035
 
 
 def test_flow_sharding_two_gpus():
