@@ -540,7 +540,8 @@ lookup_kernel(const LookupArgs a, const long n_groups) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
     const LookupLane t = lookup_lane_init(lane);
-    // grid-stride over the groups: the grid is one resident wave, so there is no tail wave of a few blocks
+    // (one group per warp: a grid-stride loop over groups makes the compiler hoist the per-group set-up out of the loop
+    // and spill it -- 300+ bytes of local memory)
     {
         const long g = static_cast<long>(blockIdx.x) * 8 + wib;
         if (g >= n_groups) return;
@@ -552,16 +553,9 @@ lookup_kernel(const LookupArgs a, const long n_groups) {
 }
 
 cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream) {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
     const long n_groups = (total + kLkGroup - 1) / kLkGroup;
-    long blocks = (n_groups + 7) / 8;
-    if (blocks > static_cast<long>(n_sm) * 5) blocks = static_cast<long>(n_sm) * 5;       // 5 resident blocks per SM (launch bounds)
+    const long blocks = (n_groups + 7) / 8;
     return launch_pdl(lookup_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a, n_groups);
 }
 
