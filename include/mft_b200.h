@@ -77,6 +77,11 @@ int mftb200_slot_buffers(mftb200_ctx* ctx, void** fmap, void** net, void** inp, 
 /* For each pair p: flow left_slots[p] -> right_slots[p].  out: device float (n_pairs,4,H,W). */
 int mftb200_raft_refine(mftb200_ctx* ctx, int n_pairs, const int* left_slots, const int* right_slots, float* out,
                         mftb200_stream stream);
+/* Same with a flow initialisation (RAFT.forward's flow_init, MFT/RAFT/core/raft.py:153-154; compute_flow's init_flow after
+ * padding and downsample_flow_8, MFT/raft.py:49-53): init_flow = device float (n_pairs,2,h,w) at the coarse resolution
+ * (h x w = padded H/8 x W/8), added to the start coordinates; NULL = none. */
+int mftb200_raft_refine_init(mftb200_ctx* ctx, int n_pairs, const int* left_slots, const int* right_slots,
+                             const float* init_flow, float* out, mftb200_stream stream);
 
 /* ---- chaining + selection (chain_results + selection block + invalid mask:
  * MFT/MFT.py:114-142,233-239; MFT/results.py:87-136,250-265) ------------------------------ */

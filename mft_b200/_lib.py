@@ -32,6 +32,7 @@ def _declare(lib):
         'mftb200_is_pinned_host': (ci, [vp]),
         'mftb200_slot_buffers': (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), vp]),
         'mftb200_raft_refine': (ci, [vp, ci, C.POINTER(ci), C.POINTER(ci), vp, vp]),
+        'mftb200_raft_refine_init': (ci, [vp, ci, C.POINTER(ci), C.POINTER(ci), vp, vp, vp]),
         'mftb200_chain_select': (ci, [ci, C.POINTER(vp), vp, cf, ci, ci, vp, vp, vp]),
         'mftb200_warp_backward': (ci, [vp, vp, ci, ci, ci, ci, vp, vp]),
         'mftb200_sample_points': (ci, [vp, ci, ci, ci, vp, ci, ci, vp, vp]),

@@ -122,6 +122,7 @@ struct mftb200_ctx {
     int corr_plan = -1, corr_bulk = 1;
     bool corr_bulk_ok = false;
     float* out_cur = nullptr;              // where the upsampling kernel writes: the caller's buffer of the current refine
+    const float* init_flow_cur = nullptr;  // optional coarse initial flow of the current refine (planar (pairs,2,h,w))
     // Deferred context encoder.  cnet(t) is only read when frame t is the LEFT image of a pair, i.e. from the next frame
     // on, so it does not have to sit on frame t's critical path: encode_frame runs fnet (+ cnet's first convolution, which
     // shares the patch matrix with fnet) and parks the rest of cnet; raft_refine enqueues it on `ctx_stream` behind its
@@ -334,7 +335,8 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;        // first pixel row of this sub-batch
         PairSetup a{cc->slot_table + 2 * cc->cur_b0, cc->fmap_slots, cc->net_slots, cc->inp_slots, cc->F1 + o * 256,
-                    cc->F2 + o * 256, cc->h32 + o * 128, cc->X + o * 512, cc->coords1 + o * 2, cc->cur_pairs, cc->h, cc->w};
+                    cc->F2 + o * 256, cc->h32 + o * 128, cc->X + o * 512, cc->coords1 + o * 2,
+                    cc->init_flow_cur ? cc->init_flow_cur + o * 2 : nullptr, cc->cur_pairs, cc->h, cc->w};
         cc->launches++;
         return cu_err(launch_pair_setup(a, s));
     });
@@ -912,6 +914,11 @@ int mftb200_is_pinned_host(const void* p) {
 
 int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, const int* right_slots, float* out,
                         mftb200_stream stream) {
+    return mftb200_raft_refine_init(c, n_pairs, left_slots, right_slots, nullptr, out, stream);
+}
+
+int mftb200_raft_refine_init(mftb200_ctx* c, int n_pairs, const int* left_slots, const int* right_slots, const float* init_flow,
+                             float* out, mftb200_stream stream) {
     if (!c) return MFTB200_ERR_ARG;
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "raft_refine: not configured");
     if (c->poisoned) return c->fail(MFTB200_ERR_DEVICE_FLAG, "raft_refine: a kernel aborted earlier; call mftb200_configure again");
@@ -936,6 +943,7 @@ int mftb200_raft_refine(mftb200_ctx* c, int n_pairs, const int* left_slots, cons
         }
     }
     c->out_cur = out;
+    c->init_flow_cur = init_flow;
     // pageable source: the runtime stages the copy before returning, so `table` may go out of scope
     if (cudaMemcpyAsync(c->slot_table, table, sizeof(int) * 2 * n_pairs, cudaMemcpyHostToDevice, s) != cudaSuccess)
         return c->fail(MFTB200_ERR_CUDA, "raft_refine: slot table copy failed");

@@ -449,7 +449,11 @@ pair_setup_kernel(const PairSetup a) {
     reinterpret_cast<uint2*>(a.X + pp * 512)[lane] = pk;
     // inp: 128 halves = 16 x uint4 -> X[:, 128:256]
     if (lane < 16) reinterpret_cast<uint4*>(a.X + pp * 512 + 128)[lane] = reinterpret_cast<const uint4*>(a.inp_slots)[lsrc * 16 + lane];
-    if (lane < 2) a.coords1[pp * 2 + lane] = static_cast<float>(lane == 0 ? n % a.w : n / a.w);
+    if (lane < 2) {
+        float c = static_cast<float>(lane == 0 ? n % a.w : n / a.w);
+        if (a.init_flow != nullptr) c = c + a.init_flow[(static_cast<long>(pair) * 2 + lane) * npx + n];
+        a.coords1[pp * 2 + lane] = c;
+    }
 }
 
 cudaError_t launch_pair_setup(const PairSetup& a, cudaStream_t stream) {

@@ -61,6 +61,7 @@ struct PairSetup {
     float* h32;                      // [pair][Npx][128]
     __half* X;                       // [pair][Npx][512]  h | inp | motion | r*h
     float* coords1;                  // [pair][Npx][2]
+    const float* init_flow;          // optional planar [pair][2][Npx] coarse flow added to the start coordinates (core/raft.py:153-154)
     int n_pairs, h, w;
 };
 cudaError_t launch_pair_setup(const PairSetup& a, cudaStream_t stream);

@@ -74,8 +74,9 @@ class Engine:
         _lib.check(self.L.mftb200_encode_frame(self.ctx, C.c_void_p(self._pinned.data_ptr()), 0, slot, _stream_ptr()), self.ctx)
         return False
 
-    def refine(self, left_slots, right_slots, out=None):
-        """Batched RAFT-OU refinement.  Returns CUDA float tensor (n_pairs, 4, H, W)."""
+    def refine(self, left_slots, right_slots, out=None, init_flow=None):
+        """Batched RAFT-OU refinement.  Returns CUDA float tensor (n_pairs, 4, H, W).
+        init_flow: optional CUDA float (n_pairs, 2, h, w) coarse flow added to the start coordinates (RAFT's flow_init)."""
         H, W = self.geometry[:2]
         n = len(left_slots)
         assert n == len(right_slots) and 1 <= n <= self.geometry[2]
@@ -83,7 +84,13 @@ class Engine:
             out = torch.empty((n, 4, H, W), dtype=torch.float32, device='cuda')
         ls = (C.c_int * n)(*[int(s) for s in left_slots])
         rs = (C.c_int * n)(*[int(s) for s in right_slots])
-        _lib.check(self.L.mftb200_raft_refine(self.ctx, n, ls, rs, C.c_void_p(out.data_ptr()), _stream_ptr()), self.ctx)
+        if init_flow is None:
+            _lib.check(self.L.mftb200_raft_refine(self.ctx, n, ls, rs, C.c_void_p(out.data_ptr()), _stream_ptr()), self.ctx)
+        else:
+            hp, wp = (H + 7) // 8, (W + 7) // 8
+            assert init_flow.is_cuda and init_flow.dtype == torch.float32 and init_flow.is_contiguous() and tuple(init_flow.shape) == (n, 2, hp, wp)
+            _lib.check(self.L.mftb200_raft_refine_init(self.ctx, n, ls, rs, C.c_void_p(init_flow.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                       _stream_ptr()), self.ctx)
         return out
 
     def slot_tensors(self):

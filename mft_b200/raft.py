@@ -60,14 +60,21 @@ class RAFTWrapper:
     def compute_flow(self, src_img, dst_img, mode='TC', vis=False, src_img_identifier=None,
                      numpy_out=False, init_flow=None, vis_debug=False):
         """src_img, dst_img: (H,W,3) uint8 BGR.  mode 'flow' or 'TC' (raft.py:30-94)."""
-        if init_flow is not None:
-            raise NotImplementedError('init_flow is never used by the tracker (MFT.py:98) and is not supported')
         H, W = src_img.shape[:2]
+        flow_init = None
+        if init_flow is not None:
+            # MFT/raft.py:49-53: replicate-pad like the images (InputPadder), then downsample_flow_8 -> RAFT's flow_init.
+            # (Host-side preparation of an optional argument: two torch ops on a (2,H,W) tensor.)
+            f = torch.as_tensor(init_flow).to('cuda', torch.float32).reshape(1, 2, H, W)
+            ph, pw = (8 - H % 8) % 8, (8 - W % 8) % 8
+            if ph or pw:
+                f = F.pad(f, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), mode='replicate')
+            flow_init = downsample_flow_8(f).contiguous()
         eng = self.ensure_geometry(H, W)
         s0 = TRACKER_SLOTS if eng is self.engine else 0        # the two scratch slots behind the tracker's ring
         in_place = eng.encode_frame(src_img, s0)
         in_place = eng.encode_frame(dst_img, s0 + 1) or in_place
-        out = eng.refine([s0], [s0 + 1])[0]
+        out = eng.refine([s0], [s0 + 1], init_flow=flow_init)[0]
         eng.error_flag_async()
         if in_place:
             eng.wait_frame_copied()

@@ -387,7 +387,7 @@ def corr_lookup_grid_sample(pyr, coords, radius=4):
     return torch.cat(out, 1).t().reshape(-1, h, w).contiguous()
 
 
-def raft_forward(W, image1, image2, iters=12, taps=None, fast_lookup=False):
+def raft_forward(W, image1, image2, iters=12, taps=None, fast_lookup=False, flow_init=None):
     """RAFT.forward(test_mode=True) (core/raft.py:97-259).  Images (1,3,H,W) float RGB in
     [0,255], H,W multiples of 8.  Returns dict(flow (1,2,H,W), occlusion logits (1,2,H,W),
     uncertainty (1,1,H,W), coords (1,2,h,w)).  ``taps``: optional dict that receives stage
@@ -399,6 +399,8 @@ def raft_forward(W, image1, image2, iters=12, taps=None, fast_lookup=False):
     _, _, h, w = fmap1.shape
     coords0 = coords_grid(h, w)
     coords1 = coords0.clone()
+    if flow_init is not None:                 # core/raft.py:153-154: (1,2,h,w) coarse flow added to the start coordinates
+        coords1 = coords1 + flow_init[0]
     if taps is not None:
         taps.update(fmap1=fmap1, fmap2=fmap2, net0=net, inp=inp, pyramid=pyr, iters=[])
     for itr in range(iters):
@@ -453,11 +455,24 @@ def postprocess(out, H, W):
     return flow, occ, sigma
 
 
-def compute_flow(W, src_bgr, dst_bgr, iters=12, taps=None, fast_lookup=False):
-    """RAFTWrapper.compute_flow(mode='flow') -> flow (2,H,W), occlusion (1,H,W), sigma (1,H,W)."""
+def downsample_flow_8(flow):
+    """MFT/raft.py:98-101: bilinear (align_corners=True) to 1/8 resolution, values / 8."""
+    return F.interpolate(flow, size=(flow.shape[2] // 8, flow.shape[3] // 8), mode='bilinear', align_corners=True) / 8
+
+
+def compute_flow(W, src_bgr, dst_bgr, iters=12, taps=None, fast_lookup=False, init_flow=None):
+    """RAFTWrapper.compute_flow(mode='flow') -> flow (2,H,W), occlusion (1,H,W), sigma (1,H,W).
+    init_flow: optional (2,H,W) flow, replicate-padded like the images and downsampled by 8 (MFT/raft.py:49-53)."""
     H, Wd = src_bgr.shape[:2]
+    flow_init = None
+    if init_flow is not None:
+        f = torch.as_tensor(init_flow, dtype=torch.float32)[None]
+        l, r, t, b = pad_amounts(H, Wd)
+        if l or r or t or b:
+            f = F.pad(f, (l, r, t, b), mode='replicate')
+        flow_init = downsample_flow_8(f)
     out = raft_forward(W, bgr_to_input(src_bgr), bgr_to_input(dst_bgr), iters=iters, taps=taps,
-                       fast_lookup=fast_lookup)
+                       fast_lookup=fast_lookup, flow_init=flow_init)
     return postprocess(out, H, Wd)
 
 

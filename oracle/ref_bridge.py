@@ -96,13 +96,17 @@ class CpuFlower:
 
     @torch.no_grad()
     def compute_flow(self, src_img, dst_img, mode='flow', init_flow=None, **kw):
-        assert mode == 'flow' and init_flow is None
+        assert mode == 'flow'
         H, W = src_img.shape[:2]
         im1 = torch.from_numpy(src_img[:, :, ::-1].copy()).permute(2, 0, 1)[None].float()
         im2 = torch.from_numpy(dst_img[:, :, ::-1].copy()).permute(2, 0, 1)[None].float()
         padder = self.InputPadder(im1.shape)
         im1, im2 = padder.pad(im1, im2)
-        pred = self.model(im1, im2, iters=self.iters, test_mode=True)
+        if init_flow is not None:                      # MFT/raft.py:49-53 with the reference's own helpers
+            from MFT.raft import downsample_flow_8
+            init_flow, = padder.pad(torch.as_tensor(init_flow, dtype=torch.float32)[None])
+            init_flow = downsample_flow_8(init_flow)
+        pred = self.model(im1, im2, iters=self.iters, test_mode=True, flow_init=init_flow)
         flow = padder.unpad(pred['flow'])[0]
         occ = torch.squeeze(padder.unpad(pred['occlusion'].softmax(dim=1)[:, 1:2]), dim=0)
         sigma = torch.sqrt(torch.exp(torch.squeeze(padder.unpad(pred['uncertainty']), dim=0)))

@@ -149,6 +149,25 @@ def test_padded_size_vs_reference_golden(seeded_weights):
     assert tuple(out.shape) == (1, 4, H, Wd) and st['epe_mean'] < 0.12 and st['epe_p995'] < 0.4 and st['occ_mean'] < 0.002, st
 
 
+def test_init_flow_vs_reference_golden(real_weights, seeded_weights):
+    """RAFTWrapper.compute_flow(init_flow=...) against the unmodified reference (MFT/raft.py:49-53, core/raft.py:153-154):
+    128x128 with the shipped checkpoint and 131x140 (odd replicate pad of the initial flow) with seeded weights."""
+    from mft_b200.config import Config
+    from mft_b200.raft import RAFTWrapper
+    g = golden('raft_init_flow.npz')
+    for tag, W, gate in (('real', real_weights, (0.01, 0.1, 5e-4)), ('pad', seeded_weights, (0.13, 0.42, 0.002))):
+        fc = Config(); fc.model = W; fc.flow_iters = 12
+        fl = RAFTWrapper(fc)
+        fr = g[f'{tag}_frames']
+        flow, extra = fl.compute_flow(fr[0], fr[1], mode='flow', init_flow=torch.from_numpy(g[f'{tag}_init']))
+        got = torch.cat([flow, extra['occlusion'], extra['sigma']])
+        st = _flow_stats(got, torch.from_numpy(g[f'{tag}_flow']), torch.from_numpy(g[f'{tag}_occ']), torch.from_numpy(g[f'{tag}_sigma']))
+        record_parity(f'init_flow_{tag}_vs_reference', st)
+        assert st['epe_mean'] < gate[0] and st['epe_p995'] < gate[1] and st['occ_mean'] < gate[2], (tag, st)
+        plain, _ = fl.compute_flow(fr[0], fr[1], mode='flow')
+        assert (plain - flow).abs().max().item() > 0.01            # the initialisation is really used
+
+
 @pytest.mark.parametrize('size', [(128, 160), (256, 256)])
 def test_corr_bulk_store_bit_identical(size, seeded_weights):
     """The correlation volume written as bulk tensor stores (fp16 blocks, 64-byte swizzle) vs per-thread stores."""

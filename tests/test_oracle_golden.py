@@ -50,6 +50,21 @@ def test_raft_padded_size_seeded(seeded_weights):
     _check_pair(g, 0, 2, seeded_weights, {0: g['frames'][0], 2: g['frames'][1]})
 
 
+def test_init_flow_vs_reference(real_weights, seeded_weights):
+    """compute_flow(init_flow=...) (MFT/raft.py:49-53, core/raft.py:153-154): replicate pad, downsample_flow_8, flow_init."""
+    g = golden('raft_init_flow.npz')
+    for tag, W in (('real', real_weights), ('pad', seeded_weights)):
+        fr = g[f'{tag}_frames']
+        flow, occ, sigma = O.compute_flow(W, fr[0], fr[1], init_flow=g[f'{tag}_init'])
+        assert np.abs(flow.numpy() - g[f'{tag}_flow']).max() < TOL_FLOW, tag
+        assert np.abs(occ.numpy() - g[f'{tag}_occ']).max() < TOL_OCC, tag
+        assert (np.abs(sigma.numpy() - g[f'{tag}_sigma']) / (1 + g[f'{tag}_sigma'])).max() < TOL_SIGMA, tag
+    # the initialisation matters: without it the result differs visibly
+    fr = g['real_frames']
+    plain, _, _ = O.compute_flow(real_weights, fr[0], fr[1])
+    assert np.abs(plain.numpy() - g['real_flow']).max() > 0.01
+
+
 def test_chain_select_vs_reference_tracker():
     """Chaining + selection + invalid mask, against MFT.track itself fed with recorded flows."""
     g = golden('chain_select.npz')
