@@ -570,7 +570,8 @@ def run_flow_shard(args):
     eng = E.Engine(weights)
     eng.configure(H, W, max_pairs=7, n_slots=n_slots, iters=iters)
     barrier = make_barrier(world)
-    own = {t: torch.from_numpy(frames[t]).cuda() for t in range(T) if t == 0 or (t - 1) % G == rank}
+    local_encode = bool(os.environ.get('BENCH_FLOWSHARD_LOCAL_ENCODE'))      # bisecting aid: every rank encodes every frame itself
+    own = {t: torch.from_numpy(frames[t]).cuda() for t in range(T) if t == 0 or (t - 1) % G == rank or local_encode}
     eng.encode_frame(own[0], 0)                                # the template: every rank encodes it itself
     feats = eng.slot_tensors()
     feat_events = []
@@ -578,6 +579,10 @@ def run_flow_shard(args):
     def encode_fn(ts):
         t0 = ts[0]
         mine = t0 + rank
+        if local_encode:
+            for t in ts:
+                eng.encode_frame(own[t], t)
+            return
         if mine in own:
             eng.encode_frame(own[mine], mine)                  # slot index == frame index
         if G > 1:
@@ -626,11 +631,18 @@ def run_flow_shard(args):
     if not args.no_identity_check:
         ref = make_tracker(weights, iters=iters)
         ref.init(frames[0])
-        ok = True
+        ok, first_bad, worst = True, -1, 0.0
         for t in range(1, T):
             want = ref.track(frames[t], device_result=True).result.packed()
-            if t > pre:
-                ok = ok and torch.equal(results[t], want)
+            if not torch.equal(results[t], want):
+                if first_bad < 0:
+                    first_bad = t
+                d = (results[t] - want).abs()
+                worst = max(worst, float(d[torch.isfinite(d)].max().item()) if torch.isfinite(d).any() else float('inf'))
+                if t > pre:
+                    ok = False
+        if first_bad >= 0:
+            print(f'[flow-shard identity] rank {rank}: first differing frame {first_bad}, largest |difference| {worst:.6g}', file=sys.stderr)
         flag = torch.tensor([1 if ok else 0], device='cuda')
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)

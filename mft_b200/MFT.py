@@ -71,7 +71,7 @@ class MFT:
             self.engine.wait_frame_copied()
         self.memory = {start_frame_i: {'img': img, 'slot': slot,
                                        'result': FlowOUTrackingResult.identity((self.img_H, self.img_W), device=self.device)}}
-        self.template_img = img.copy()
+        self.template_img = img.clone() if isinstance(img, torch.Tensor) else img.copy()      # (device-resident frames: bench / tapvid)
         meta = SimpleNamespace()
         meta.result = self.memory[start_frame_i]['result'].clone().cpu()
         return meta

@@ -101,6 +101,9 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
 // instruction, clipped by TMA) instead of per-thread st.global.  Needs one-row tiles (GEMM view) and a dense row-major
 // output.  Returns nullptr when enabled or the reason why not.
 const char* conv_plan_enable_tma_store(ConvPlan* p, long rows);
+// Plain (un-swizzled, zero-filled, no L2 promotion) fp16 tensor map of `rank` dims; strides_bytes has rank - 1 entries.
+const char* encode_tensor_map_plain(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
+                                    const unsigned long long* strides_bytes, const unsigned* box);
 
 // Test / tuning override for the cluster size chosen by conv_plan_init (0 = automatic).
 void conv_set_forced_cluster(int c);

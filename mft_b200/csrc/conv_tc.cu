@@ -1281,6 +1281,22 @@ static const char* encode(CUtensorMap* tm, const void* base, int rank, const cuu
     return nullptr;
 }
 
+// Un-swizzled fp16 tensor map (zero fill outside the tensor, no L2 promotion): small gather boxes such as the lookup's
+// 16 x 10 correlation windows.
+const char* encode_tensor_map_plain(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
+                                    const unsigned long long* strides_bytes, const unsigned* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return "cuTensorMapEncodeTiled entry point not available";
+    cuuint64_t d[5], st[5];
+    cuuint32_t b[5], es[5];
+    if (rank < 1 || rank > 5) return "encode_tensor_map_plain: bad rank";
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; if (i + 1 < rank) st[i] = strides_bytes[i]; }
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, st, b, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : "encode_tensor_map_plain: cuTensorMapEncodeTiled failed";
+}
+
 const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a_cin, int in_H, int in_W, int batch,
                            int stride, const TapList& taps, const __half* wt, int cout_pad, int n_tile,
                            int b_rows_per_batch, int force_tile_h, int force_tile_w) {

@@ -113,6 +113,11 @@ struct mftb200_ctx {
     long long* prog_timing = nullptr;      // role timers of the program kernel, written only with option "prog_timing"
     bool prog_ok = false, prog_full_ok = false;
     int lookup_step = -1;
+    // pyramid levels as 3-D tensor maps for the TMA lookup (needs w % 64 == 0: every level's row pitch a multiple of 16 bytes)
+    CUtensorMap lk_tm[4];
+    bool lk_tma_ok = false;
+    int lookup_tma = 1;
+    int lookup_l2_keep = 0;
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
@@ -376,6 +381,12 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
                      cc->coords1 + o * 2, cc->corr16 + o * 328, cc->flowpatch + o * 104, cc->X + o * 512, cc->cur_pairs,
                      cc->h, cc->w};
         cc->launches++;
+        if (cc->lk_tma_ok && cc->lookup_tma) {
+            LookupTmaArgs t;
+            for (int l = 0; l < 4; ++l) t.tm[l] = cc->lk_tm[l];
+            t.a = a; t.pix0 = static_cast<int>(o); t.err_flag = cc->err_flag; t.l2_keep = cc->lookup_l2_keep;
+            return cu_err(launch_lookup_tma(t, s));
+        }
         return cu_err(launch_lookup(a, s));
     });
     Act a_corr{c->corr16, 328, 324, h, w};
@@ -792,6 +803,13 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
         chk(c->corr[l] = c->dalloc<__half>(M * hl * wl));
         hl /= 2; wl /= 2;
     }
+    c->lk_tma_ok = ok && (c->w % 64) == 0 && M * npx < (1ull << 40);
+    for (int l = 0; l < 4 && c->lk_tma_ok; ++l) {
+        const unsigned long long wl2 = c->w >> l, hl2 = c->h >> l;
+        const unsigned long long dims[3] = {wl2, hl2, M}, strides[2] = {wl2 * 2, wl2 * hl2 * 2};
+        const unsigned box[3] = {24, 10, 1};          // kLtBoxCols x 10 rows (kernels.cu)
+        c->lk_tma_ok = encode_tensor_map_plain(&c->lk_tm[l], c->corr[l], 3, dims, strides, box) == nullptr;
+    }
     chk(c->corr16 = c->dalloc<__half>(M * 328));
     chk(c->flowpatch = c->dalloc<__half>(M * 104));
     chk(c->c1buf = c->dalloc<__half>(M * 256));
@@ -1109,6 +1127,8 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
         return MFTB200_OK;
     }
     if (strcmp(key, "defer_context") == 0) { c->defer_context = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "lookup_tma") == 0) { c->lookup_tma = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "lookup_l2_keep") == 0) { c->lookup_l2_keep = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()

@@ -3,6 +3,7 @@
 // operation, no contraction) so that results are bit-identical to oracle/mft_oracle.py.
 #include "kernels.h"
 #include "lookup.cuh"
+#include "ptx.cuh"
 
 #include <cmath>
 
@@ -561,6 +562,148 @@ cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream) {
     const long n_groups = (total + kLkGroup - 1) / kLkGroup;
     const long blocks = (n_groups + 7) / 8;
     return launch_pdl(lookup_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a, n_groups);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA variant.  One warp per group of kLkGroup consecutive (pair, source pixel)s, as above, but the 16 windows of a group
+// (4 pixels x 4 levels) are 16 bulk tensor copies issued by lanes 0..15 (lane p * 4 + l: the lane that evaluated the
+// position of (pixel p, level l)) onto the warp's own mbarrier.  While they are in flight the warp writes the flow
+// operands (7x7x2 neighbourhood for convf1, flow channels of the GRU record); then each level's boxes are widened to the
+// fp32 window layout of lookup_blend_level and blended exactly as in lookup_group: same bits.
+// ------------------------------------------------------------------------------------------
+constexpr int kLtWarps = 4;
+// The innermost box coordinate of a bulk tensor copy must be a multiple of 16 bytes (anything else raises "illegal
+// instruction" on the B200: tools/tma_box_probe.cu), so a window that starts at column X0 is fetched from column X0 & ~7:
+// its 10 columns then sit at offset X0 & 7 <= 7 of a 24-column box.
+constexpr int kLtBoxCols = 24;
+constexpr int kLtBoxBytes = 512;                          // a 24 x 10 fp16 box is 480 bytes; destinations are 128-byte aligned
+constexpr int kLtBoxTx = kLtBoxCols * 10 * 2;
+
+__global__ void __launch_bounds__(kLtWarps * 32)
+lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) {
+    __shared__ __align__(128) unsigned char boxes[kLtWarps][16 * kLtBoxBytes];
+    __shared__ __align__(16) float win[kLtWarps][kLkWinFloats];
+    __shared__ __align__(8) uint64_t bar[kLtWarps];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        mbar_init(&bar[wib], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    pdl_enter();
+    const long g = static_cast<long>(blockIdx.x) * kLtWarps + wib;
+    if (g >= n_groups) return;
+    const LookupArgs& a = P.a;
+    const int npx = a.h * a.w;
+    const long total = static_cast<long>(a.n_pairs) * npx;
+    const long pp0 = g * kLkGroup;
+    const int nvalid = total - pp0 < kLkGroup ? static_cast<int>(total - pp0) : kLkGroup;
+    const unsigned valid_mask = (1u << nvalid) - 1u;
+
+    // ---- set-up: lane p * 4 + l evaluates (pixel p, level l), as in lookup_group -----------------------------------------
+    const int sp = (lane >> 2) & (kLkGroup - 1), sl = lane & 3;
+    const bool sv = sp < nvalid;
+    const long spp = pp0 + (sv ? sp : 0);
+    const float2 c = __ldcg(reinterpret_cast<const float2*>(a.coords1 + spp * 2));
+    const int my_finite = (isfinite(c.x) && isfinite(c.y)) ? 1 : 0;
+    const int mh = a.h >> sl, mw = a.w >> sl;
+    const float inv = 1.0f / static_cast<float>(1 << sl);
+    const float fxp = lk_roundtrip_div(c.x * inv - 4.0f, static_cast<float>(mw - 1));
+    const float fyp = lk_roundtrip_div(c.y * inv - 4.0f, static_cast<float>(mh - 1));
+    const float fx = floorf(fxp), fy = floorf(fyp);
+    const float my_wE = fxp - fx, my_wS = fyp - fy;
+    const int my_X0 = my_finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(mw + 16))) : -64;
+    const int my_Y0 = my_finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(mh + 16))) : -64;
+    const int my_n = static_cast<int>(static_cast<unsigned>(spp) % static_cast<unsigned>(npx));      // (total < 2^31)
+    const int my_y = my_n / a.w, my_x = my_n - my_y * a.w;
+
+    // ---- the 16 windows --------------------------------------------------------------------------------------------------
+    unsigned char* mybox = boxes[wib];
+    if (lane == 0) mbar_arrive_expect_tx(&bar[wib], static_cast<uint32_t>(nvalid) * 4u * kLtBoxTx);
+    __syncwarp();
+    if (lane < 16 && sv) {
+        if (P.l2_keep) tma_load_3d_hint(mybox + lane * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp), l2_policy_evict_last());
+        else tma_load_3d(mybox + lane * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp));
+    }
+    const int my_a4 = my_X0 & 4;                                           // first box column of the widened window (0 | 4)
+
+    // ---- flow operands while the windows are in flight: lane = tap (ky * 7 + kx) of the 7x7 neighbourhood, both channels.
+    //      All eight loads of the group are issued before the first store (the compiler cannot prove that the fp16
+    //      outputs do not alias coords1, so loads behind a store would wait for it: eight L2 round trips in a row).
+    {
+        const int t0 = lane, t1 = lane + 32;                               // taps 0..31 and 32..51 (49..51: zero pad of the row)
+        const int ky0 = (t0 * 37) >> 8, ky1 = (t1 * 37) >> 8;             // tap / 7 (tap < 64)
+        const int dx0 = t0 - ky0 * 7 - 3, dy0 = ky0 - 3, dx1 = t1 - ky1 * 7 - 3, dy1 = ky1 - 3;
+        float2 f0[kLkGroup], f1[kLkGroup];
+        float bx0[kLkGroup], by0[kLkGroup], bx1[kLkGroup], by1[kLkGroup];
+        unsigned in_mask = 0;
+#pragma unroll
+        for (int p = 0; p < kLkGroup; ++p) {
+            const int x = __shfl_sync(0xffffffffu, my_x, p * 4), y = __shfl_sync(0xffffffffu, my_y, p * 4);
+            const float2* cb = reinterpret_cast<const float2*>(a.coords1) + (pp0 + (p < nvalid ? p : 0) - (y * a.w + x));
+            const unsigned xa = static_cast<unsigned>(x + dx0), ya = static_cast<unsigned>(y + dy0);
+            const unsigned xb = static_cast<unsigned>(x + dx1), yb = static_cast<unsigned>(y + dy1);
+            const bool ia = xa < static_cast<unsigned>(a.w) && ya < static_cast<unsigned>(a.h);
+            const bool ib = lane < 17 && xb < static_cast<unsigned>(a.w) && yb < static_cast<unsigned>(a.h);
+            f0[p] = __ldcg(cb + (ia ? ya * static_cast<unsigned>(a.w) + xa : 0u));
+            f1[p] = __ldcg(cb + (ib ? yb * static_cast<unsigned>(a.w) + xb : 0u));
+            bx0[p] = static_cast<float>(xa); by0[p] = static_cast<float>(ya);
+            bx1[p] = static_cast<float>(xb); by1[p] = static_cast<float>(yb);
+            in_mask |= (ia ? 1u : 0u) << (2 * p) | (ib ? 2u : 0u) << (2 * p);
+        }
+#pragma unroll
+        for (int p = 0; p < kLkGroup; ++p) {
+            if (p < nvalid) {
+                const long pp = pp0 + p;
+                unsigned* fp = reinterpret_cast<unsigned*>(a.flowpatch16 + pp * 104);
+                const bool ia = (in_mask >> (2 * p)) & 1u, ib = (in_mask >> (2 * p + 1)) & 1u;
+                const __half2 ha = __floats2half2_rn(ia ? f0[p].x - bx0[p] : 0.0f, ia ? f0[p].y - by0[p] : 0.0f);
+                const __half2 hb = __floats2half2_rn(ib ? f1[p].x - bx1[p] : 0.0f, ib ? f1[p].y - by1[p] : 0.0f);
+                fp[t0] = *reinterpret_cast<const unsigned*>(&ha);
+                if (lane == 24) *reinterpret_cast<unsigned*>(a.X + pp * 512 + 382) = *reinterpret_cast<const unsigned*>(&ha);
+                if (lane < 20) fp[t1] = *reinterpret_cast<const unsigned*>(&hb);
+                if (lane == 0) *reinterpret_cast<uint2*>(a.corr16 + pp * 328 + 324) = make_uint2(0u, 0u);
+            }
+        }
+    }
+
+    // ---- widen + blend, level by level --------------------------------------------------------------------------------------
+    // widening task T = lane + 32 r (T < 160): (pixel p, window row, 4-element chunk c) -> floats 4c .. 4c+3 of row (p, row) of
+    // the fp32 window [pixel][row][16] = box columns a4 + 4c ..; the window proper starts at float X0 & 3 of its rows
+    int src_off[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const int T = lane + 32 * r;
+        const int p = T / 40, rem = T - p * 40, row = rem >> 2, ch = rem & 3;
+        src_off[r] = p * 4 * kLtBoxBytes + row * (kLtBoxCols * 2) + ch * 8;
+    }
+    if (!mbar_wait(&bar[wib], 0)) {
+        if (lane == 0 && P.err_flag != nullptr) atomicExch(P.err_flag, 90);
+        return;
+    }
+    float* w = win[wib];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        __syncwarp();                                                      // the previous level's blend is done with the window buffer
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const int T = lane + 32 * r;
+            const int a4 = __shfl_sync(0xffffffffu, my_a4, (T / 40) * 4 + l);
+            const uint2 v = *reinterpret_cast<const uint2*>(mybox + l * kLtBoxBytes + src_off[r] + a4 * 2);
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            *reinterpret_cast<float4*>(w + T * 4) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        }
+        __syncwarp();
+        lookup_blend_level<4>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_X0 & 3, my_finite, lane, w);
+    }
+}
+
+cudaError_t launch_lookup_tma(const LookupTmaArgs& a, cudaStream_t stream) {
+    const long total = static_cast<long>(a.a.n_pairs) * a.a.h * a.a.w;
+    const long n_groups = (total + kLkGroup - 1) / kLkGroup;
+    const long blocks = (n_groups + kLtWarps - 1) / kLtWarps;
+    return launch_pdl(lookup_tma_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kLtWarps * 32), 0, stream, a, n_groups);
 }
 
 // ==========================================================================================

@@ -3,6 +3,7 @@
 // launch's cudaError_t (checked by the engine).
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -78,6 +79,19 @@ struct LookupArgs {
     int n_pairs, h, w;
 };
 cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream);
+
+// The same lookup with the correlation windows fetched by the TMA unit: level l of the pyramid is a 3-D fp16 tensor
+// (x: w_l, y: h_l, row: pair * Npx + n); ONE 24 x 10 box per (pixel, level), starting at a multiple of 8 columns, lands in shared memory, out-of-map taps arrive
+// as zeros (= grid_sample's zero padding), no per-element address arithmetic or bounds handling in the SM.  Needs every
+// level's width to be a multiple of 8 (16-byte row pitch).  Bit-identical to launch_lookup.
+struct LookupTmaArgs {
+    CUtensorMap tm[4];
+    LookupArgs a;                    // a.lvl is not read; the other pointers start at row pix0
+    int pix0;                        // first row of this launch in the tensor maps
+    int l2_keep;                     // 1: fetch the windows with the L2 evict_last priority (they are re-read every iteration)
+    int* err_flag;                   // raised when a window never arrives (bounded wait)
+};
+cudaError_t launch_lookup_tma(const LookupTmaArgs& a, cudaStream_t stream);
 
 struct OuPackArgs {
     const __half* X; const __half* corr16; const float* coords1; const float* delta32;

@@ -268,6 +268,35 @@ def test_persistent_program_bit_identical(geom, seeded_weights):
             assert torch.equal(ref1, got1), (geom, mode, rep)
 
 
+@pytest.mark.parametrize('geom', [(512, 512, 3), (512, 1024, 2)])
+def test_tma_lookup_bit_identical(geom, seeded_weights):
+    """The pyramid lookup with TMA-fetched windows (one 16 x 10 box per (pixel, level), zero fill outside the map; used when
+    the coarse width is a multiple of 64) against the per-element gather kernel: same blend arithmetic, so the lookup
+    output of the last iteration and the final fields must agree bit for bit."""
+    from mft_b200.synth import synthetic_video
+    H, Wd, pairs = geom
+    frames = list(synthetic_video(pairs + 1, H, Wd, seed=31))
+    eng = _engine(seeded_weights, H, Wd, pairs=pairs, slots=pairs + 1)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    lefts, rights = list(range(pairs)), [pairs] * pairs
+    M = pairs * (H // 8) * (Wd // 8)
+    res = {}
+    for tma in (1, 0, 1):
+        eng.set_option('lookup_tma', tma)
+        out = eng.refine(lefts, rights).clone()
+        eng.check_device()
+        c16 = eng.debug_buffer('corr16', torch.float16, (M, 328)).clone()
+        fpt = eng.debug_buffer('flowpatch', torch.float16, (M, 104)).clone()
+        if tma in res:
+            assert torch.equal(res[tma][0], out)                       # repeatable
+        res[tma] = (out, c16, fpt)
+    assert torch.isfinite(res[1][1].float()).all() and res[1][1].float().abs().max().item() > 0.1
+    assert torch.equal(res[1][1], res[0][1]), (res[1][1].float() - res[0][1].float()).abs().max().item()
+    assert torch.equal(res[1][2], res[0][2])
+    assert torch.equal(res[1][0], res[0][0])
+
+
 def test_program_column_split_bit_identical(seeded_weights):
     """Global option prog_split_n: the 256-column layers of the iteration program (convc1, z|r, flow head 1) as two
     128-column work items per tile.  An output column's K order does not depend on the column tiling, so not a single bit

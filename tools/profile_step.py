@@ -18,6 +18,9 @@ weights, _ = bench.load_weights()
 trk = bench.make_tracker(weights)
 frames = [torch.from_numpy(f).cuda() for f in synthetic_video(bench.STEADY + 4 + steps, size, size, seed=1234)]
 trk.init(frames[0].cpu().numpy())
+for kv in filter(None, os.environ.get('BENCH_ENGINE_OPTIONS', '').split(',')):      # same A/B knobs as bench.py
+    k, v = kv.split('=')
+    trk.engine.set_option(k.strip(), int(v))
 t = 1
 for _ in range(bench.STEADY + 2):
     trk.track(frames[t], device_result=True)
