@@ -633,8 +633,10 @@ int run_steps_groups(mftb200_ctx* c, std::vector<mftb200_ctx::Step>& steps, cons
 }
 
 // Enqueues the parked part of the context encoder on ctx_stream, ordered after everything queued on `after` so far.
-// wait_on != nullptr: that stream then waits for the context (it is about to read it).
-int flush_context(mftb200_ctx* c, cudaStream_t after, cudaStream_t wait_on) {
+// wait: `after` then waits for the context (it is about to read it).  (A flag, not a null stream: the caller's stream is
+// usually stream 0, the legacy default stream, whose handle IS the null pointer.)
+int flush_context(mftb200_ctx* c, cudaStream_t after, bool wait) {
+    cudaStream_t wait_on = after;
     if (c->pending_ctx_slot >= 0) {
         const int keep = c->cur_slot;
         c->cur_slot = c->pending_ctx_slot;
@@ -651,7 +653,7 @@ int flush_context(mftb200_ctx* c, cudaStream_t after, cudaStream_t wait_on) {
         c->ctx_done_valid = true;
         c->cur_slot = keep;
     }
-    if (wait_on != nullptr && c->ctx_done_valid) cudaStreamWaitEvent(wait_on, c->ev_ctx_done, 0);
+    if (wait && c->ctx_done_valid) cudaStreamWaitEvent(wait_on, c->ev_ctx_done, 0);
     return MFTB200_OK;
 }
 
@@ -873,7 +875,7 @@ int mftb200_encode_frame(mftb200_ctx* c, const uint8_t* bgr, int on_device, int 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     c->last_main = s;
     // a context still parked (two encodes without a refine in between) goes first: it reads cnet's activation buffers
-    if (int r = flush_context(c, s, nullptr)) return r;
+    if (int r = flush_context(c, s, false)) return r;
     const size_t bytes = static_cast<size_t>(c->H) * c->W * 3;
     if (cudaMemcpyAsync(c->frame_u8, bgr, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s) !=
         cudaSuccess)
@@ -912,7 +914,7 @@ int mftb200_slot_buffers(mftb200_ctx* c, void** fmap, void** net, void** inp, si
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the context encoder of the newest frame may still be parked / running on the engine's own stream: `stream` is
     // ordered behind it, so that a collective enqueued there sees complete slots
-    if (int r = flush_context(c, s, s)) return r;
+    if (int r = flush_context(c, s, true)) return r;
     *fmap = c->fmap_slots; *net = c->net_slots; *inp = c->inp_slots;
     slot_bytes[0] = static_cast<size_t>(c->npx) * 256 * sizeof(__half);
     slot_bytes[1] = static_cast<size_t>(c->npx) * 128 * sizeof(float);
@@ -955,7 +957,7 @@ int mftb200_raft_refine_init(mftb200_ctx* c, int n_pairs, const int* left_slots,
         bool need = false;
         for (int p = 0; p < n_pairs; ++p) need = need || left_slots[p] == c->pending_ctx_slot;
         if (need || c->profile) {
-            if (int r = flush_context(c, s, s)) return r;
+            if (int r = flush_context(c, s, true)) return r;
         } else if (c->ctx_done_valid) {
             cudaStreamWaitEvent(s, c->ev_ctx_done, 0);
         }
@@ -1036,7 +1038,7 @@ int mftb200_raft_refine_init(mftb200_ctx* c, int n_pairs, const int* left_slots,
     c->cur_pairs = n_pairs;
     if (r != MFTB200_OK) return r;
     // the parked context encoder of the newest frame runs behind this call's work (nothing here reads it)
-    return flush_context(c, s, nullptr);
+    return flush_context(c, s, false);
 }
 
 int mftb200_chain_select(int K, const float* const* left, const float* right, float occlusion_threshold, int H, int W,
@@ -1183,7 +1185,7 @@ int mftb200_profile_fetch(mftb200_ctx* c, double* ms_by_kind, long long* steps_b
 int mftb200_debug_buffer(mftb200_ctx* c, const char* name, void** ptr, size_t* bytes) {
     if (!c || !name || !ptr || !bytes) return MFTB200_ERR_ARG;
     if (!c->configured) return c->fail(MFTB200_ERR_STATE, "debug_buffer: not configured");
-    if (c->pending_ctx_slot >= 0) flush_context(c, c->last_main, c->last_main);      // (last_main may be stream 0, the default stream)
+    if (c->pending_ctx_slot >= 0) flush_context(c, c->last_main, true);      // (last_main may be stream 0, the default stream)
     const size_t npx = c->npx, M = npx * c->max_pairs;
     struct Ent { const char* n; void* p; size_t b; };
     const Ent tab[] = {

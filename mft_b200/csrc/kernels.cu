@@ -581,8 +581,11 @@ constexpr int kLtBoxTx = kLtBoxCols * 10 * 2;
 
 __global__ void __launch_bounds__(kLtWarps * 32)
 lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) {
-    __shared__ __align__(128) unsigned char boxes[kLtWarps][16 * kLtBoxBytes];
-    __shared__ __align__(16) float win[kLtWarps][kLkWinFloats];
+    // Per warp: 16 box slots, level major (slot = level * 4 + pixel), + 512 bytes.  The levels are processed 3, 2, 1, 0 and the
+    // fp32 window of level l (2560 bytes) is written over the boxes of level l itself (read into registers first) and the
+    // first quarter of level l + 1's, which are dead by then: 8.5 KiB per warp instead of 10.5, i.e. six blocks per SM and
+    // the 1792 blocks of a 512x512 / 7-pair launch in two waves instead of 2.4.
+    __shared__ __align__(128) unsigned char boxes[kLtWarps][16 * kLtBoxBytes + 512];
     __shared__ __align__(8) uint64_t bar[kLtWarps];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
@@ -622,8 +625,9 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
     if (lane == 0) mbar_arrive_expect_tx(&bar[wib], static_cast<uint32_t>(nvalid) * 4u * kLtBoxTx);
     __syncwarp();
     if (lane < 16 && sv) {
-        if (P.l2_keep) tma_load_3d_hint(mybox + lane * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp), l2_policy_evict_last());
-        else tma_load_3d(mybox + lane * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp));
+        const int slot = sl * 4 + sp;
+        if (P.l2_keep) tma_load_3d_hint(mybox + slot * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp), l2_policy_evict_last());
+        else tma_load_3d(mybox + slot * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp));
     }
     const int my_a4 = my_X0 & 4;                                           // first box column of the widened window (0 | 4)
 
@@ -675,23 +679,29 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
     for (int r = 0; r < 5; ++r) {
         const int T = lane + 32 * r;
         const int p = T / 40, rem = T - p * 40, row = rem >> 2, ch = rem & 3;
-        src_off[r] = p * 4 * kLtBoxBytes + row * (kLtBoxCols * 2) + ch * 8;
+        src_off[r] = p * kLtBoxBytes + row * (kLtBoxCols * 2) + ch * 8;
     }
     if (!mbar_wait(&bar[wib], 0)) {
         if (lane == 0 && P.err_flag != nullptr) atomicExch(P.err_flag, 90);
         return;
     }
-    float* w = win[wib];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        __syncwarp();                                                      // the previous level's blend is done with the window buffer
+    for (int l = 3; l >= 0; --l) {
+        unsigned char* region = mybox + l * 4 * kLtBoxBytes;
+        float* w = reinterpret_cast<float*>(region);
+        uint2 v[5];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
             const int T = lane + 32 * r;
             const int a4 = __shfl_sync(0xffffffffu, my_a4, (T / 40) * 4 + l);
-            const uint2 v = *reinterpret_cast<const uint2*>(mybox + l * kLtBoxBytes + src_off[r] + a4 * 2);
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            v[r] = *reinterpret_cast<const uint2*>(region + src_off[r] + a4 * 2);
+        }
+        __syncwarp();                                                      // every box of this level is in registers: the window may overwrite them
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const int T = lane + 32 * r;
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v[r].x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v[r].y));
             *reinterpret_cast<float4*>(w + T * 4) = make_float4(f0.x, f0.y, f1.x, f1.y);
         }
         __syncwarp();

@@ -212,6 +212,32 @@ def test_pinned_frame_is_read_in_place(seeded_weights):
     assert dnet <= 1e-5 * max(1.0, float(net.abs().max())), dnet
 
 
+def test_parked_context_is_ordered_before_its_readers(seeded_weights):
+    """The context encoder of the newest frame is parked behind the frame's refinement (engine option defer_context).
+    Everything that reads it earlier must be ordered behind it ON THE CALLER'S STREAM -- also when that is stream 0, the
+    legacy default stream, whose handle is a null pointer: (a) work enqueued after slot_tensors() (a collective that ships
+    the feature slots to another rank), (b) a refinement that uses the newest frame as its LEFT image."""
+    from mft_b200.synth import synthetic_video
+    frames = list(synthetic_video(6, 256, 256, seed=12))
+    eng = _engine(seeded_weights, 256, 256, pairs=2, slots=6)
+    eng.encode_frame(frames[0], 0)
+    feats = eng.slot_tensors()
+    for t in range(1, 6):
+        eng.encode_frame(frames[t], t)
+        eng.slot_tensors()
+        snaps = [x[t].clone() for x in feats]                 # enqueued on the caller's stream right behind slot_tensors()
+        torch.cuda.synchronize()
+        for name, snap, x in zip(('fmap', 'net', 'inp'), snaps, feats):
+            assert torch.equal(snap, x[t]), (t, name)
+    eng.encode_frame(frames[0], 0)
+    eng.encode_frame(frames[1], 1)
+    first = eng.refine([1], [0]).clone()                      # left image = the frame whose context is still parked
+    torch.cuda.synchronize()
+    again = eng.refine([1], [0]).clone()
+    eng.check_device()
+    assert torch.equal(first, again)
+
+
 def test_batched_equals_single_pair(seeded_weights):
     """A pair's result must not depend on what else is in the batch (bit-exact)."""
     from mft_b200.synth import synthetic_video
