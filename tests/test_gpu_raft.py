@@ -155,7 +155,7 @@ def test_init_flow_vs_reference_golden(real_weights, seeded_weights):
     from mft_b200.config import Config
     from mft_b200.raft import RAFTWrapper
     g = golden('raft_init_flow.npz')
-    for tag, W, gate in (('real', real_weights, (0.01, 0.1, 5e-4)), ('pad', seeded_weights, (0.13, 0.42, 0.002))):
+    for tag, W, gate in (('real', real_weights, (0.005, 0.06, 3e-4)), ('pad', seeded_weights, (0.125, 0.42, 0.0017))):
         fc = Config(); fc.model = W; fc.flow_iters = 12
         fl = RAFTWrapper(fc)
         fr = g[f'{tag}_frames']
@@ -163,6 +163,7 @@ def test_init_flow_vs_reference_golden(real_weights, seeded_weights):
         got = torch.cat([flow, extra['occlusion'], extra['sigma']])
         st = _flow_stats(got, torch.from_numpy(g[f'{tag}_flow']), torch.from_numpy(g[f'{tag}_occ']), torch.from_numpy(g[f'{tag}_sigma']))
         record_parity(f'init_flow_{tag}_vs_reference', st)
+        # measured: real EPE mean 0.0017 px, p99.5 0.021 px, occlusion 1e-4; padded / seeded 0.043 px, 0.18 px, 5.7e-4 (gates <= 3x)
         assert st['epe_mean'] < gate[0] and st['epe_p995'] < gate[1] and st['occ_mean'] < gate[2], (tag, st)
         plain, _ = fl.compute_flow(fr[0], fr[1], mode='flow')
         assert (plain - flow).abs().max().item() > 0.01            # the initialisation is really used
