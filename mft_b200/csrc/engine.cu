@@ -117,7 +117,6 @@ struct mftb200_ctx {
     CUtensorMap lk_tm[4];
     bool lk_tma_ok = false;
     int lookup_tma = 1;
-    int lookup_l2_keep = 0;
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
@@ -384,7 +383,7 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         if (cc->lk_tma_ok && cc->lookup_tma) {
             LookupTmaArgs t;
             for (int l = 0; l < 4; ++l) t.tm[l] = cc->lk_tm[l];
-            t.a = a; t.pix0 = static_cast<int>(o); t.err_flag = cc->err_flag; t.l2_keep = cc->lookup_l2_keep;
+            t.a = a; t.pix0 = static_cast<int>(o); t.err_flag = cc->err_flag;
             return cu_err(launch_lookup_tma(t, s));
         }
         return cu_err(launch_lookup(a, s));
@@ -1130,7 +1129,6 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     }
     if (strcmp(key, "defer_context") == 0) { c->defer_context = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "lookup_tma") == 0) { c->lookup_tma = value ? 1 : 0; return MFTB200_OK; }
-    if (strcmp(key, "lookup_l2_keep") == 0) { c->lookup_l2_keep = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()

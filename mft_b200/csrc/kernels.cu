@@ -541,7 +541,7 @@ cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L
 __global__ void __launch_bounds__(256, 5)
 lookup_kernel(const LookupArgs a, const long n_groups) {
     pdl_enter();
-    __shared__ __align__(16) float win[8][kLkWinFloats];
+    __shared__ __align__(16) float win[8][kLkGroup * 10 * 20];        // window row pitch 20 floats: no bank conflicts in the blend
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long total = static_cast<long>(a.n_pairs) * a.h * a.w;
     const LookupLane t = lookup_lane_init(lane);
@@ -552,7 +552,7 @@ lookup_kernel(const LookupArgs a, const long n_groups) {
         if (g >= n_groups) return;
         const long pp0 = g * kLkGroup;
         const long left = total - pp0;
-        lookup_group(a, t, pp0, left < kLkGroup ? static_cast<int>(left) : kLkGroup, lane, win[wib]);
+        lookup_group<20>(a, t, pp0, left < kLkGroup ? static_cast<int>(left) : kLkGroup, lane, win[wib]);
         __syncwarp();
     }
 }
@@ -579,19 +579,21 @@ constexpr int kLtBoxCols = 24;
 constexpr int kLtBoxBytes = 512;                          // a 24 x 10 fp16 box is 480 bytes; destinations are 128-byte aligned
 constexpr int kLtBoxTx = kLtBoxCols * 10 * 2;
 
-__global__ void __launch_bounds__(kLtWarps * 32)
+constexpr int kLtWinPitch = 20;                           // floats per fp32 window row: 20 (not 16) keeps the blends free of bank conflicts
+constexpr int kLtRegion = kLkGroup * 10 * kLtWinPitch * 4; // the fp32 window of one level (3200 bytes), laid over the level's four boxes (2048 bytes)
+
+__global__ void __launch_bounds__(kLtWarps * 32, 8)
 lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) {
-    // Per warp: 16 box slots, level major (slot = level * 4 + pixel), + 512 bytes.  The levels are processed 3, 2, 1, 0 and the
-    // fp32 window of level l (2560 bytes) is written over the boxes of level l itself (read into registers first) and the
-    // first quarter of level l + 1's, which are dead by then: 8.5 KiB per warp instead of 10.5, i.e. six blocks per SM and
-    // the 1792 blocks of a 512x512 / 7-pair launch in two waves instead of 2.4.
-    __shared__ __align__(128) unsigned char boxes[kLtWarps][16 * kLtBoxBytes + 512];
-    __shared__ __align__(8) uint64_t bar[kLtWarps];
+    // Per warp: two regions of four box slots (+ 512 bytes each) and two mbarriers.  The levels run 3, 2, 1, 0; level l uses
+    // region l & 1.  Levels 3 and 2 are fetched first; level 1 is fetched into region 1 as soon as level 3 has been blended
+    // and level 0 into region 0 after level 2, so their latency runs under the blends in between.  The fp32 window of a level
+    // (3200 bytes, row pitch 20 floats) is written over the level's own boxes (read into registers first) and the spare bytes
+    // behind them: 6.25 KiB of shared memory per warp.
+    __shared__ __align__(128) unsigned char boxes[kLtWarps][2 * kLtRegion];
+    __shared__ __align__(8) uint64_t bar[kLtWarps][2];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        mbar_init(&bar[wib], 1);
-        fence_mbar_init();
-    }
+    if (lane < 2) mbar_init(&bar[wib][lane], 1);
+    if (lane == 0) fence_mbar_init();
     __syncwarp();
     pdl_enter();
     const long g = static_cast<long>(blockIdx.x) * kLtWarps + wib;
@@ -617,52 +619,51 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
     const float my_wE = fxp - fx, my_wS = fyp - fy;
     const int my_X0 = my_finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(mw + 16))) : -64;
     const int my_Y0 = my_finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(mh + 16))) : -64;
-    const int my_n = static_cast<int>(static_cast<unsigned>(spp) % static_cast<unsigned>(npx));      // (total < 2^31)
-    const int my_y = my_n / a.w, my_x = my_n - my_y * a.w;
-
-    // ---- the 16 windows --------------------------------------------------------------------------------------------------
-    unsigned char* mybox = boxes[wib];
-    if (lane == 0) mbar_arrive_expect_tx(&bar[wib], static_cast<uint32_t>(nvalid) * 4u * kLtBoxTx);
-    __syncwarp();
-    if (lane < 16 && sv) {
-        const int slot = sl * 4 + sp;
-        if (P.l2_keep) tma_load_3d_hint(mybox + slot * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp), l2_policy_evict_last());
-        else tma_load_3d(mybox + slot * kLtBoxBytes, &P.tm[sl], &bar[wib], my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp));
-    }
     const int my_a4 = my_X0 & 4;                                           // first box column of the widened window (0 | 4)
+
+    // ---- window fetch: the lanes (p, level) of one level issue its four boxes onto the level's region / barrier ---------------
+    unsigned char* mybox = boxes[wib];
+    const uint32_t level_tx = static_cast<uint32_t>(nvalid) * kLtBoxTx;
+    auto fetch = [&](int l) {
+        uint64_t* b = &bar[wib][l & 1];
+        if (lane == 0) mbar_arrive_expect_tx(b, level_tx);
+        __syncwarp();
+        if (lane < 16 && sl == l && sv)
+            tma_load_3d(mybox + (l & 1) * kLtRegion + sp * kLtBoxBytes, &P.tm[l], b, my_X0 & ~7, my_Y0, P.pix0 + static_cast<int>(spp));
+    };
+    fetch(3);
+    fetch(2);
 
     // ---- flow operands while the windows are in flight: lane = tap (ky * 7 + kx) of the 7x7 neighbourhood, both channels.
     //      All eight loads of the group are issued before the first store (the compiler cannot prove that the fp16
     //      outputs do not alias coords1, so loads behind a store would wait for it: eight L2 round trips in a row).
+    //      (The four pixels of a group are consecutive in one image row: the coarse width is a multiple of 64 here.)
     {
+        const int n0 = static_cast<int>(static_cast<unsigned>(pp0) % static_cast<unsigned>(npx));      // (total < 2^31)
+        const int y = n0 / a.w, x0 = n0 - y * a.w;
         const int t0 = lane, t1 = lane + 32;                               // taps 0..31 and 32..51 (49..51: zero pad of the row)
         const int ky0 = (t0 * 37) >> 8, ky1 = (t1 * 37) >> 8;             // tap / 7 (tap < 64)
-        const int dx0 = t0 - ky0 * 7 - 3, dy0 = ky0 - 3, dx1 = t1 - ky1 * 7 - 3, dy1 = ky1 - 3;
+        const int dx0 = t0 - ky0 * 7 - 3, dx1 = t1 - ky1 * 7 - 3;
+        const unsigned ya = static_cast<unsigned>(y + ky0 - 3), yb = static_cast<unsigned>(y + ky1 - 3);
+        const bool rowa = ya < static_cast<unsigned>(a.h), rowb = lane < 17 && yb < static_cast<unsigned>(a.h);
+        const float2* cb = reinterpret_cast<const float2*>(a.coords1) + (pp0 - n0);
         float2 f0[kLkGroup], f1[kLkGroup];
-        float bx0[kLkGroup], by0[kLkGroup], bx1[kLkGroup], by1[kLkGroup];
-        unsigned in_mask = 0;
 #pragma unroll
         for (int p = 0; p < kLkGroup; ++p) {
-            const int x = __shfl_sync(0xffffffffu, my_x, p * 4), y = __shfl_sync(0xffffffffu, my_y, p * 4);
-            const float2* cb = reinterpret_cast<const float2*>(a.coords1) + (pp0 + (p < nvalid ? p : 0) - (y * a.w + x));
-            const unsigned xa = static_cast<unsigned>(x + dx0), ya = static_cast<unsigned>(y + dy0);
-            const unsigned xb = static_cast<unsigned>(x + dx1), yb = static_cast<unsigned>(y + dy1);
-            const bool ia = xa < static_cast<unsigned>(a.w) && ya < static_cast<unsigned>(a.h);
-            const bool ib = lane < 17 && xb < static_cast<unsigned>(a.w) && yb < static_cast<unsigned>(a.h);
+            const unsigned xa = static_cast<unsigned>(x0 + p + dx0), xb = static_cast<unsigned>(x0 + p + dx1);
+            const bool ia = rowa && xa < static_cast<unsigned>(a.w), ib = rowb && xb < static_cast<unsigned>(a.w);
             f0[p] = __ldcg(cb + (ia ? ya * static_cast<unsigned>(a.w) + xa : 0u));
             f1[p] = __ldcg(cb + (ib ? yb * static_cast<unsigned>(a.w) + xb : 0u));
-            bx0[p] = static_cast<float>(xa); by0[p] = static_cast<float>(ya);
-            bx1[p] = static_cast<float>(xb); by1[p] = static_cast<float>(yb);
-            in_mask |= (ia ? 1u : 0u) << (2 * p) | (ib ? 2u : 0u) << (2 * p);
         }
 #pragma unroll
         for (int p = 0; p < kLkGroup; ++p) {
             if (p < nvalid) {
                 const long pp = pp0 + p;
                 unsigned* fp = reinterpret_cast<unsigned*>(a.flowpatch16 + pp * 104);
-                const bool ia = (in_mask >> (2 * p)) & 1u, ib = (in_mask >> (2 * p + 1)) & 1u;
-                const __half2 ha = __floats2half2_rn(ia ? f0[p].x - bx0[p] : 0.0f, ia ? f0[p].y - by0[p] : 0.0f);
-                const __half2 hb = __floats2half2_rn(ib ? f1[p].x - bx1[p] : 0.0f, ib ? f1[p].y - by1[p] : 0.0f);
+                const unsigned xa = static_cast<unsigned>(x0 + p + dx0), xb = static_cast<unsigned>(x0 + p + dx1);
+                const bool ia = rowa && xa < static_cast<unsigned>(a.w), ib = rowb && xb < static_cast<unsigned>(a.w);
+                const __half2 ha = __floats2half2_rn(ia ? f0[p].x - static_cast<float>(xa) : 0.0f, ia ? f0[p].y - static_cast<float>(ya) : 0.0f);
+                const __half2 hb = __floats2half2_rn(ib ? f1[p].x - static_cast<float>(xb) : 0.0f, ib ? f1[p].y - static_cast<float>(yb) : 0.0f);
                 fp[t0] = *reinterpret_cast<const unsigned*>(&ha);
                 if (lane == 24) *reinterpret_cast<unsigned*>(a.X + pp * 512 + 382) = *reinterpret_cast<const unsigned*>(&ha);
                 if (lane < 20) fp[t1] = *reinterpret_cast<const unsigned*>(&hb);
@@ -673,21 +674,22 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
 
     // ---- widen + blend, level by level --------------------------------------------------------------------------------------
     // widening task T = lane + 32 r (T < 160): (pixel p, window row, 4-element chunk c) -> floats 4c .. 4c+3 of row (p, row) of
-    // the fp32 window [pixel][row][16] = box columns a4 + 4c ..; the window proper starts at float X0 & 3 of its rows
-    int src_off[5];
+    // the fp32 window [pixel][row][20] = box columns a4 + 4c ..; the window proper starts at float X0 & 3 of its rows
+    int src_off[5], dst_off[5];
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         const int T = lane + 32 * r;
         const int p = T / 40, rem = T - p * 40, row = rem >> 2, ch = rem & 3;
         src_off[r] = p * kLtBoxBytes + row * (kLtBoxCols * 2) + ch * 8;
-    }
-    if (!mbar_wait(&bar[wib], 0)) {
-        if (lane == 0 && P.err_flag != nullptr) atomicExch(P.err_flag, 90);
-        return;
+        dst_off[r] = (p * 10 + row) * kLtWinPitch + ch * 4;
     }
 #pragma unroll
     for (int l = 3; l >= 0; --l) {
-        unsigned char* region = mybox + l * 4 * kLtBoxBytes;
+        if (!mbar_wait(&bar[wib][l & 1], l < 2 ? 1u : 0u)) {               // (each barrier completes twice: levels 3 | 2, then 1 | 0)
+            if (lane == 0 && P.err_flag != nullptr) atomicExch(P.err_flag, 90);
+            return;
+        }
+        unsigned char* region = mybox + (l & 1) * kLtRegion;
         float* w = reinterpret_cast<float*>(region);
         uint2 v[5];
 #pragma unroll
@@ -702,10 +704,15 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
             const int T = lane + 32 * r;
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v[r].x));
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v[r].y));
-            *reinterpret_cast<float4*>(w + T * 4) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            *reinterpret_cast<float4*>(w + dst_off[r]) = make_float4(f0.x, f0.y, f1.x, f1.y);
         }
         __syncwarp();
-        lookup_blend_level<4>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_X0 & 3, my_finite, lane, w);
+        lookup_blend_level<4, kLtWinPitch>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_X0 & 3, my_finite, lane, w);
+        if (l >= 2) {
+            __syncwarp();                                                  // the blend is done with the region
+            fence_proxy_async_smem();                                      // ... before the TMA unit writes it again
+            fetch(l - 2);
+        }
     }
 }
 

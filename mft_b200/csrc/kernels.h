@@ -88,7 +88,6 @@ struct LookupTmaArgs {
     CUtensorMap tm[4];
     LookupArgs a;                    // a.lvl is not read; the other pointers start at row pix0
     int pix0;                        // first row of this launch in the tensor maps
-    int l2_keep;                     // 1: fetch the windows with the L2 evict_last priority (they are re-read every iteration)
     int* err_flag;                   // raised when a window never arrives (bounded wait)
 };
 cudaError_t launch_lookup_tma(const LookupTmaArgs& a, cudaStream_t stream);

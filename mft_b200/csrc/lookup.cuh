@@ -102,14 +102,14 @@ __device__ __forceinline__ void lookup_load_level(const __half* __restrict__ bas
 }
 
 // Converts the chunks to fp32 and stores them into the group's window buffer [pixel][row][kPitch].
-template <int VEC>
+template <int VEC, int PITCH = LkChunks<VEC>::kPitch>
 __device__ __forceinline__ void lookup_store_level(const LkRegs& c, int lane, float* win) {
     using C = LkChunks<VEC>;
 #pragma unroll
     for (int r = 0; r < C::kRounds; ++r) {
         const int T = r * 32 + lane;
         if (T < C::kTasks) {
-            float* dst = win + T * VEC;
+            float* dst = win + (PITCH == C::kPitch ? T * VEC : (T / C::kPerRow) * PITCH + (T % C::kPerRow) * VEC);
             if constexpr (VEC == 4) {
                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[2 * r]));
                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&c.w[2 * r + 1]));
@@ -143,10 +143,12 @@ __device__ __forceinline__ void lk_store9(__half* dst, const float (&o)[9], bool
 // Round A: lane = (pixel p, output column i < 8): the whole column, 10 horizontal + 9 vertical lerps.  Round B: the ninth
 // column of the four pixels, one output per lane (36 outputs: lanes 0..31, then lanes 0..3) -- a second column round would
 // keep 4 of 32 lanes busy.
-template <int VEC>
+// PITCH: floats per window row (the gather's chunk geometry by default; the TMA variant uses 20: with 16 the four pixels of
+// round A and the rows of round B fall into the same shared-memory banks, 4- to 5-way conflicts).
+template <int VEC, int PITCH = LkChunks<VEC>::kPitch>
 __device__ __forceinline__ void lookup_blend_level(__half* __restrict__ corr16, long pp0, unsigned valid_mask, int l, float my_wE, float my_wS,
                                                    int my_off, int my_finite, int lane, const float* win) {
-    constexpr int pitch = LkChunks<VEC>::kPitch;
+    constexpr int pitch = PITCH;
     {
         const int p = lane >> 3, i = lane & 7;
         const int src = p * 4 + l;
@@ -188,8 +190,10 @@ __device__ __forceinline__ void lookup_blend_level(__half* __restrict__ corr16, 
 __device__ __forceinline__ int lookup_vec(int wl) { return (wl & 3) == 0 ? 4 : ((wl & 1) == 0 ? 2 : 1); }
 
 // The whole lookup of pixels pp0 .. pp0 + nvalid - 1 (global pixel indices pair * h*w + n; nvalid <= kLkGroup) by one warp.
-// `win`: this warp's kLkWinFloats floats of shared memory.  coords1 may have been written earlier in the same launch by
+// `win`: this warp's kLkGroup * 10 * PITCH4 floats of shared memory; PITCH4 = floats per window row for the 8-byte-chunk
+// geometry (widths that are multiples of 4): 16 = dense, 20 = free of bank conflicts in the blend (25 % more shared memory).  coords1 may have been written earlier in the same launch by
 // another CTA: read through L2.
+template <int PITCH4 = 16>
 __device__ __forceinline__ void lookup_group(const LookupArgs& a, const LookupLane& t, long pp0, int nvalid, int lane, float* win) {
     const unsigned valid_mask = (1u << nvalid) - 1u;
     const int npx = a.h * a.w;
@@ -229,12 +233,12 @@ __device__ __forceinline__ void lookup_group(const LookupArgs& a, const LookupLa
     for (int l = 0; l < 4; ++l) {
         const int v = lookup_vec(a.w >> l);
         __syncwarp();                      // the previous level's blend is done with the buffer
-        if (v == 4) lookup_store_level<4>(regs, lane, win);
+        if (v == 4) lookup_store_level<4, PITCH4>(regs, lane, win);
         else if (v == 2) lookup_store_level<2>(regs, lane, win);
         else lookup_store_level<1>(regs, lane, win);
         if (l < 3) load(l + 1);
         __syncwarp();
-        if (v == 4) lookup_blend_level<4>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
+        if (v == 4) lookup_blend_level<4, PITCH4>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
         else if (v == 2) lookup_blend_level<2>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
         else lookup_blend_level<1>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_off, my_finite, lane, win);
     }
