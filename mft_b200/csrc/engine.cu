@@ -286,14 +286,20 @@ const char* build_encoder(mftb200_ctx* c, Builder& B, int net, std::vector<mftb2
         Act atmp{tmp, b.cout, b.cout, Ho, Wo};
         const __half* res = in;
         if (inorm) {
-            S.push_back(B.step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
-            norm(c->raw, Po, b.cout, 1, nullptr, tmp);
             if (b.ds >= 0) {
+                // the 1x1 down-sampling branch only shares the block input with conv1 -> norm -> conv2: it runs on the side
+                // stream (free while fnet runs: cnet is deferred) and is joined before the block's last norm adds it
+                S.push_back(sync_step(1));
                 S.push_back(B.step(B.conv16(net + b.ds, ain, 1, b.stride, t1, b.cout, 0, c->raw2, b.cout, 0, b.cout), false));
+                S.back().lane = 1;
                 norm(c->raw2, Po, b.cout, 0, nullptr, xd);
+                S.back().lane = 1;
                 res = xd;
             }
+            S.push_back(B.step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
+            norm(c->raw, Po, b.cout, 1, nullptr, tmp);
             S.push_back(B.step(B.conv16(net + b.c2, atmp, 1, 1, t3, b.cout, 0, c->raw, b.cout, 0, b.cout), false));
+            if (b.ds >= 0) S.push_back(sync_step(2));
             norm(c->raw, Po, b.cout, 1, res, out);
         } else {
             S.push_back(B.step(B.conv16(net + b.c1, ain, 1, b.stride, t3, b.cout, 1, tmp, b.cout, 0, b.cout), false));
