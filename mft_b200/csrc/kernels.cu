@@ -590,6 +590,9 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
     // (3200 bytes, row pitch 20 floats) is written over the level's own boxes (read into registers first) and the spare bytes
     // behind them: 6.25 KiB of shared memory per warp.
     __shared__ __align__(128) unsigned char boxes[kLtWarps][2 * kLtRegion];
+    // the group's four output rows (328 fp16 each) are collected here and leave as 16-byte stores of one contiguous 2624-byte run
+    // (written per level from the blend they were 2- and 4-byte stores at an 18-byte stride: ~8 L1 wavefronts per instruction)
+    __shared__ __align__(16) __half outrow[kLtWarps][kLkGroup * 328];
     __shared__ __align__(8) uint64_t bar[kLtWarps][2];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane < 2) mbar_init(&bar[wib][lane], 1);
@@ -667,10 +670,11 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
                 fp[t0] = *reinterpret_cast<const unsigned*>(&ha);
                 if (lane == 24) *reinterpret_cast<unsigned*>(a.X + pp * 512 + 382) = *reinterpret_cast<const unsigned*>(&ha);
                 if (lane < 20) fp[t1] = *reinterpret_cast<const unsigned*>(&hb);
-                if (lane == 0) *reinterpret_cast<uint2*>(a.corr16 + pp * 328 + 324) = make_uint2(0u, 0u);
             }
         }
     }
+    __half* orow = outrow[wib];
+    if (lane < kLkGroup) *reinterpret_cast<uint2*>(orow + lane * 328 + 324) = make_uint2(0u, 0u);      // channels 324..327: zero pad
 
     // ---- widen + blend, level by level --------------------------------------------------------------------------------------
     // widening task T = lane + 32 r (T < 160): (pixel p, window row, 4-element chunk c) -> floats 4c .. 4c+3 of row (p, row) of
@@ -707,11 +711,22 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
             *reinterpret_cast<float4*>(w + dst_off[r]) = make_float4(f0.x, f0.y, f1.x, f1.y);
         }
         __syncwarp();
-        lookup_blend_level<4, kLtWinPitch>(a.corr16, pp0, valid_mask, l, my_wE, my_wS, my_X0 & 3, my_finite, lane, w);
+        lookup_blend_level<4, kLtWinPitch>(orow, 0, valid_mask, l, my_wE, my_wS, my_X0 & 3, my_finite, lane, w);
         if (l >= 2) {
             __syncwarp();                                                  // the blend is done with the region
             fence_proxy_async_smem();                                      // ... before the TMA unit writes it again
             fetch(l - 2);
+        }
+    }
+    __syncwarp();
+    {
+        uint4* dst = reinterpret_cast<uint4*>(a.corr16 + pp0 * 328);
+        const uint4* src = reinterpret_cast<const uint4*>(orow);
+        const int n16 = nvalid * 41;                                       // 656 bytes per row
+#pragma unroll
+        for (int r = 0; r < (kLkGroup * 41 + 31) / 32; ++r) {
+            const int T = lane + 32 * r;
+            if (T < n16) dst[T] = src[T];
         }
     }
 }
