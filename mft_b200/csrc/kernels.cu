@@ -486,13 +486,16 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + (2 * y + 1) * w) + g);
             const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
             __half r[4];
+            float rf[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&av[j]));
                 const float2 u = __half22float2(*reinterpret_cast<const __half2*>(&bv[j]));
                 r[j] = __float2half_rn((((t.x + t.y) + u.x) + u.y) * 0.25f);
-                s1[y * w1 + 4 * g + j] = __half2float(r[j]);
+                rf[j] = __half2float(r[j]);
             }
+            // (one 16-byte store: four scalar stores at a 4-word stride were 4-way bank conflicts; w1 is a multiple of 4 here)
+            *reinterpret_cast<float4*>(s1 + y * w1 + 4 * g) = make_float4(rf[0], rf[1], rf[2], rf[3]);
             const __half2 p01 = __halves2half2(r[0], r[1]), p23 = __halves2half2(r[2], r[3]);
             *reinterpret_cast<uint2*>(L1 + row * h1 * w1 + y * w1 + 4 * g) =
                 make_uint2(*reinterpret_cast<const uint32_t*>(&p01), *reinterpret_cast<const uint32_t*>(&p23));
@@ -510,7 +513,15 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
     for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
         const int y = i / w2, x = i % w2;
         const float* q = s1 + (2 * y) * w1 + 2 * x;
-        const __half r = __float2half_rn((((q[0] + q[1]) + q[w1]) + q[w1 + 1]) * 0.25f);
+        float2 t, u;
+        if ((w1 & 1) == 0) {                                               // even row pitch: the pairs are 8-byte aligned
+            t = *reinterpret_cast<const float2*>(q);
+            u = *reinterpret_cast<const float2*>(q + w1);
+        } else {
+            t = make_float2(q[0], q[1]);
+            u = make_float2(q[w1], q[w1 + 1]);
+        }
+        const __half r = __float2half_rn((((t.x + t.y) + u.x) + u.y) * 0.25f);
         s2[i] = __half2float(r);
         L2[row * h2 * w2 + i] = r;
     }
