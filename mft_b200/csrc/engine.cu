@@ -81,6 +81,7 @@ struct mftb200_ctx {
     float *h32 = nullptr, *z32 = nullptr, *coords1 = nullptr,
           *delta32 = nullptr, *mask32 = nullptr, *ou32 = nullptr;
     size_t corr_bytes[4] = {0, 0, 0, 0};
+    int corr_pitch[4] = {0, 0, 0, 0};      // row pitch of each pyramid level (elements): w, then (w >> l) rounded up to 8 (zero pad)
 
     std::vector<ConvPlan> plans;
     std::vector<int> plan_layer;
@@ -365,12 +366,14 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     }
     c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
-        const size_t n0 = static_cast<size_t>(cc->h) * cc->w, n1 = static_cast<size_t>(cc->h / 2) * (cc->w / 2),
-                     n2 = static_cast<size_t>(cc->h / 4) * (cc->w / 4), n3 = static_cast<size_t>(cc->h / 8) * (cc->w / 8);
+        size_t n[4];
+        for (int l = 0; l < 4; ++l) n[l] = static_cast<size_t>(cc->h >> l) * cc->corr_pitch[l];
         cc->launches++;
-        return cu_err(launch_corr_pool(cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3,
-                                       static_cast<long>(cc->cur_pairs) * cc->npx, cc->h, cc->w, s));
+        return cu_err(launch_corr_pool(cc->corr[0] + o * n[0], cc->corr[1] + o * n[1], cc->corr[2] + o * n[2], cc->corr[3] + o * n[3],
+                                       static_cast<long>(cc->cur_pairs) * cc->npx, cc->h, cc->w, cc->corr_pitch[1], cc->corr_pitch[2],
+                                       cc->corr_pitch[3], s));
     });
+
 
     // ---- one GRU iteration (core/raft.py:173-184, core/update.py:229-238) ------------------
     // Full-width tiles when the coarse map is a power of two wide (64x64 at 512^2: tiles of 2 rows x 64): the 1x5 GRU
@@ -380,9 +383,10 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
     auto& S = c->iter_steps;
     S.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
-        const size_t n0 = static_cast<size_t>(cc->h) * cc->w, n1 = static_cast<size_t>(cc->h / 2) * (cc->w / 2),
-                     n2 = static_cast<size_t>(cc->h / 4) * (cc->w / 4), n3 = static_cast<size_t>(cc->h / 8) * (cc->w / 8);
-        LookupArgs a{{cc->corr[0] + o * n0, cc->corr[1] + o * n1, cc->corr[2] + o * n2, cc->corr[3] + o * n3},
+        size_t n[4];
+        for (int l = 0; l < 4; ++l) n[l] = static_cast<size_t>(cc->h >> l) * cc->corr_pitch[l];
+        LookupArgs a{{cc->corr[0] + o * n[0], cc->corr[1] + o * n[1], cc->corr[2] + o * n[2], cc->corr[3] + o * n[3]},
+                     {cc->corr_pitch[0], cc->corr_pitch[1], cc->corr_pitch[2], cc->corr_pitch[3]},
                      cc->coords1 + o * 2, cc->corr16 + o * 328, cc->flowpatch + o * 104, cc->X + o * 512, cc->cur_pairs,
                      cc->h, cc->w};
         cc->launches++;
@@ -496,7 +500,8 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
         const char* pe = build(c->prog, depsA, 0, true);
         if (!pe) c->prog_ok = finish(c->prog, 1);
         memset(&c->prog_full, 0, sizeof c->prog_full);
-        LookupArgs lk{{c->corr[0], c->corr[1], c->corr[2], c->corr[3]}, c->coords1, c->corr16, c->flowpatch, c->X, mp, h, w};
+        LookupArgs lk{{c->corr[0], c->corr[1], c->corr[2], c->corr[3]}, {c->corr_pitch[0], c->corr_pitch[1], c->corr_pitch[2], c->corr_pitch[3]},
+                      c->coords1, c->corr16, c->flowpatch, c->X, mp, h, w};
         // the lookup (layer 0) consumes the PREVIOUS iteration's flow head 2 = the last program layer
         int n_conv_layers = 0;
         for (int k = 0; k < 11; ++k) n_conv_layers += c->plans[pi[k]].g.n_tiles;
@@ -804,16 +809,19 @@ int mftb200_configure(mftb200_ctx* c, int H, int W, int max_pairs, int n_slots, 
     chk(c->slot_table = c->dalloc<int>(2 * MFTB200_MAX_PAIRS));
     chk(c->F1 = c->dalloc<__half>(M * 256));
     chk(c->F2 = c->dalloc<__half>(M * 256));
-    int hl = c->h, wl = c->w;
     for (int l = 0; l < 4; ++l) {
-        c->corr_bytes[l] = M * hl * wl * sizeof(__half);
-        chk(c->corr[l] = c->dalloc<__half>(M * hl * wl));
-        hl /= 2; wl /= 2;
+        // pooled levels get a row pitch that is a multiple of 8 elements (16 bytes: what a tensor map needs); the pad columns are
+        // never written and stay zero, which is what a tap outside the map reads
+        c->corr_pitch[l] = l == 0 ? c->w : ((c->w >> l) + 7) / 8 * 8;
+        const size_t n = M * static_cast<size_t>(c->h >> l) * c->corr_pitch[l];
+        c->corr_bytes[l] = n * sizeof(__half);
+        chk(c->corr[l] = c->dalloc<__half>(n));
     }
-    c->lk_tma_ok = ok && (c->w % 64) == 0 && M * npx < (1ull << 40);
+    // TMA lookup: level 0's rows (w elements) must be 16-byte multiples too, and its groups of four pixels one image row
+    c->lk_tma_ok = ok && (c->w % 8) == 0 && (c->w >> 3) >= 1 && (c->h >> 3) >= 1 && M * npx < (1ull << 40);
     for (int l = 0; l < 4 && c->lk_tma_ok; ++l) {
-        const unsigned long long wl2 = c->w >> l, hl2 = c->h >> l;
-        const unsigned long long dims[3] = {wl2, hl2, M}, strides[2] = {wl2 * 2, wl2 * hl2 * 2};
+        const unsigned long long wl2 = c->w >> l, hl2 = c->h >> l, pl2 = c->corr_pitch[l];
+        const unsigned long long dims[3] = {wl2, hl2, M}, strides[2] = {pl2 * 2, pl2 * hl2 * 2};
         const unsigned box[3] = {24, 10, 1};          // kLtBoxCols x 10 rows (kernels.cu)
         c->lk_tma_ok = encode_tensor_map_plain(&c->lk_tm[l], c->corr[l], 3, dims, strides, box) == nullptr;
     }

@@ -467,7 +467,7 @@ cudaError_t launch_pair_setup(const PairSetup& a, cudaStream_t stream) {
 // ==========================================================================================
 __global__ void __launch_bounds__(256)
 corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half* __restrict__ L2, __half* __restrict__ L3,
-                 int h, int w) {
+                 int h, int w, int p1, int p2, int p3) {
     pdl_enter();
     extern __shared__ float sm[];
     const int h1 = h / 2, w1 = w / 2, h2 = h1 / 2, w2 = w1 / 2, h3 = h2 / 2, w3 = w2 / 2;
@@ -497,7 +497,7 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
             // (one 16-byte store: four scalar stores at a 4-word stride were 4-way bank conflicts; w1 is a multiple of 4 here)
             *reinterpret_cast<float4*>(s1 + y * w1 + 4 * g) = make_float4(rf[0], rf[1], rf[2], rf[3]);
             const __half2 p01 = __halves2half2(r[0], r[1]), p23 = __halves2half2(r[2], r[3]);
-            *reinterpret_cast<uint2*>(L1 + row * h1 * w1 + y * w1 + 4 * g) =
+            *reinterpret_cast<uint2*>(L1 + (row * h1 + y) * p1 + 4 * g) =
                 make_uint2(*reinterpret_cast<const uint32_t*>(&p01), *reinterpret_cast<const uint32_t*>(&p23));
         }
     } else {
@@ -506,7 +506,7 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
             const __half* q = src + (2 * y) * w + 2 * x;
             const __half r = __float2half_rn((((__half2float(q[0]) + __half2float(q[1])) + __half2float(q[w])) + __half2float(q[w + 1])) * 0.25f);
             s1[i] = __half2float(r);
-            L1[row * h1 * w1 + i] = r;
+            L1[(row * h1 + y) * p1 + x] = r;
         }
     }
     __syncthreads();
@@ -523,24 +523,25 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
         }
         const __half r = __float2half_rn((((t.x + t.y) + u.x) + u.y) * 0.25f);
         s2[i] = __half2float(r);
-        L2[row * h2 * w2 + i] = r;
+        L2[(row * h2 + y) * p2 + x] = r;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < h3 * w3; i += blockDim.x) {
         const int y = i / w3, x = i % w3;
         const float* q = s2 + (2 * y) * w2 + 2 * x;
-        L3[row * h3 * w3 + i] = __float2half_rn((((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f);
+        L3[(row * h3 + y) * p3 + x] = __float2half_rn((((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f);
     }
 }
 
-cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream) {
+cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, int p1, int p2, int p3,
+                             cudaStream_t stream) {
     const size_t smem = sizeof(float) * (static_cast<size_t>(h / 2) * (w / 2) + static_cast<size_t>(h / 4) * (w / 4));
     static bool attr = false;
     if (!attr) {
         if (cudaError_t e = cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) return e;
         attr = true;
     }
-    return launch_pdl(corr_pool_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), smem, stream, L0, L1, L2, L3, h, w);
+    return launch_pdl(corr_pool_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), smem, stream, L0, L1, L2, L3, h, w, p1, p2, p3);
 }
 
 // ==========================================================================================

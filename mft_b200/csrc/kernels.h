@@ -68,10 +68,13 @@ struct PairSetup {
 cudaError_t launch_pair_setup(const PairSetup& a, cudaStream_t stream);
 
 // 2x2 average pooling of the correlation volume over the target dims: L0 [rows][h*w] -> L1..L3.
-cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, cudaStream_t stream);
+// p1..p3: row pitch (elements) of the pooled levels (>= their width; the pad columns are never written and stay zero).
+cudaError_t launch_corr_pool(const __half* L0, __half* L1, __half* L2, __half* L3, long rows, int h, int w, int p1, int p2, int p3,
+                             cudaStream_t stream);
 
 struct LookupArgs {
-    const __half* lvl[4];            // pyramid levels [pair*Npx + n][h_l*w_l], fp16
+    const __half* lvl[4];            // pyramid levels [pair*Npx + n][h_l][pitch_l], fp16
+    int pitch[4];                    // row pitch of each level in elements: w for level 0, (w >> l) rounded up to 8 below (zero pad)
     const float* coords1;            // [pair][Npx][2]
     __half* corr16;                  // [pair*Npx][328]  (324 used)
     __half* flowpatch16;             // [pair*Npx][104]  (98 used): 7x7x2 neighbourhood of the flow

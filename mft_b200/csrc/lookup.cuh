@@ -212,16 +212,18 @@ __device__ __forceinline__ void lookup_group(const LookupArgs& a, const LookupLa
     // non-finite coordinates: park the window outside the map, every tap then reads as zero (the output is NaN anyway)
     const int my_X0 = my_finite ? static_cast<int>(fminf(fmaxf(fx, -32.0f), static_cast<float>(mw + 16))) : -64;
     const int my_Y0 = my_finite ? static_cast<int>(fminf(fmaxf(fy, -32.0f), static_cast<float>(mh + 16))) : -64;
-    const int vec_mine = lookup_vec(mw);
+    // (a level is addressed by its row pitch: the pad columns hold zeros, exactly what an out-of-map tap reads)
+    const int vec_mine = lookup_vec(sl == 0 ? a.pitch[0] : (sl == 1 ? a.pitch[1] : (sl == 2 ? a.pitch[2] : a.pitch[3])));
     const int my_off = my_X0 - (vec_mine == 4 ? (my_X0 & ~3) : (vec_mine == 2 ? (my_X0 & ~1) : my_X0));
 
     // ---- levels: the loads of level l + 1 are in flight while level l is blended -------------------------------------------------
     // (the three vector widths are separate instantiations; a level's width is warp-uniform)
     LkRegs regs;
     auto load = [&](int l) {
-        const int hl = a.h >> l, wl = a.w >> l;
+        const int hl = a.h >> l;
         // (no dynamic indexing of the kernel parameter: that would force a local-memory copy of the whole struct)
         const __half* lv = l == 0 ? a.lvl[0] : (l == 1 ? a.lvl[1] : (l == 2 ? a.lvl[2] : a.lvl[3]));
+        const int wl = l == 0 ? a.pitch[0] : (l == 1 ? a.pitch[1] : (l == 2 ? a.pitch[2] : a.pitch[3]));       // row pitch
         const __half* base0 = lv + pp0 * (static_cast<long>(hl) * wl);
         const int v = lookup_vec(wl);
         if (v == 4) lookup_load_level<4>(base0, hl, wl, valid_mask, l, my_X0, my_Y0, lane, regs);
@@ -231,7 +233,7 @@ __device__ __forceinline__ void lookup_group(const LookupArgs& a, const LookupLa
     load(0);
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        const int v = lookup_vec(a.w >> l);
+        const int v = lookup_vec(l == 0 ? a.pitch[0] : (l == 1 ? a.pitch[1] : (l == 2 ? a.pitch[2] : a.pitch[3])));
         __syncwarp();                      // the previous level's blend is done with the buffer
         if (v == 4) lookup_store_level<4, PITCH4>(regs, lane, win);
         else if (v == 2) lookup_store_level<2>(regs, lane, win);

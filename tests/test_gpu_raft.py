@@ -68,8 +68,11 @@ def test_stage_boundaries_128(tag, request):
     eng.refine([0], [1])
     eng.check_device()
     for lvl, n in enumerate((256, 64, 16, 4)):
-        c = eng.debug_buffer(f'corr_l{lvl}', torch.float16, (npx, n)).float().cpu()
-        assert _rel(c, taps['pyramid'][lvl].reshape(npx, n)) < 0.005, lvl
+        wl = 16 >> lvl                                           # 128x128 frame: coarse grid 16x16
+        pitch = wl if lvl == 0 else (wl + 7) // 8 * 8            # pooled levels: row pitch rounded up to 8 elements, zero pad
+        c = eng.debug_buffer(f'corr_l{lvl}', torch.float16, (npx, wl, pitch)).float().cpu()
+        assert (c[:, :, wl:] == 0).all(), lvl
+        assert _rel(c[:, :, :wl].reshape(npx, n), taps['pyramid'][lvl].reshape(npx, n)) < 0.005, lvl
     it0 = taps['iters'][0]
     c16 = eng.debug_buffer('corr16', torch.float16, (npx, 328)).float().cpu()
     assert _rel(c16[:, :324], _nhwc(it0['corr'])) < 0.005 and (c16[:, 324:] == 0).all()
@@ -295,10 +298,10 @@ def test_persistent_program_bit_identical(geom, seeded_weights):
             assert torch.equal(ref1, got1), (geom, mode, rep)
 
 
-@pytest.mark.parametrize('geom', [(512, 512, 3), (512, 1024, 2)])
+@pytest.mark.parametrize('geom', [(512, 512, 3), (512, 1024, 2), (264, 320, 2), (128, 192, 3)])
 def test_tma_lookup_bit_identical(geom, seeded_weights):
-    """The pyramid lookup with TMA-fetched windows (one 16 x 10 box per (pixel, level), zero fill outside the map; used when
-    the coarse width is a multiple of 64) against the per-element gather kernel: same blend arithmetic, so the lookup
+    """The pyramid lookup with TMA-fetched windows (one 24 x 10 box per (pixel, level), zero fill outside the map; used when
+    the coarse width is a multiple of 8: 320 -> 40 columns with pooled levels of 20 / 10 / 5 columns in rows of 24 / 16 / 8) against the per-element gather kernel: same blend arithmetic, so the lookup
     output of the last iteration and the final fields must agree bit for bit."""
     from mft_b200.synth import synthetic_video
     H, Wd, pairs = geom
