@@ -101,6 +101,9 @@ const char* conv_plan_init(ConvPlan* p, const __half* a_base, int a_pitch, int a
 // instruction, clipped by TMA) instead of per-thread st.global.  Needs one-row tiles (GEMM view) and a dense row-major
 // output.  Returns nullptr when enabled or the reason why not.
 const char* conv_plan_enable_tma_store(ConvPlan* p, long rows);
+// The all-pairs correlation plan (bulk-store enabled, 256 channels, 256-column slices) through the persistent kernel: resident
+// source tile, streamed target slices, double-buffered accumulators.  Bit-identical to conv_launch of the same plan.
+const char* corr_gemm_launch(const ConvPlan& p, int nbatch, int b0, cudaStream_t stream);
 // Plain (un-swizzled, zero-filled, no L2 promotion) fp16 tensor map of `rank` dims; strides_bytes has rank - 1 entries.
 const char* encode_tensor_map_plain(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
                                     const unsigned long long* strides_bytes, const unsigned* box);

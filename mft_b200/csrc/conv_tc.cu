@@ -1479,6 +1479,202 @@ static const char* launch_mode(const ConvPlan& p, int nbatch, cudaStream_t strea
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
 }
 
+// ------------------------------------------------------------------------------------------
+// persistent all-pairs correlation GEMM (core/corr.py:53-69): D[n1, n2] = <F1[n1,:], F2[n2,:]> * scale, fp16 out
+// ------------------------------------------------------------------------------------------
+// conv_tc_kernel runs the volume as (source tile, target slice) CTAs of four K stages each: at 1080p 226 k CTAs whose
+// set-up + operand fill + epilogue chain (~10 us, two co-resident) never overlaps (7.9 ms, 0.5 PFLOP/s, 2 TB/s written).
+// Here one CTA per SM stays resident and walks work items (pair, 128-pixel source tile, group of kCorrGroup target slices):
+//   * the source tile (128 x 256 channels, 64 KiB) is loaded ONCE per item and stays in shared memory for all its slices;
+//   * the target slices (256 x 64-channel stages of 32 KiB) stream through a 3-stage ring;
+//   * two 256-column TMEM accumulators: the 8 epilogue warps drain slice s (scale, fp16, 32 x 32 bulk tensor stores: the
+//     bulk-store branch of tile_epilogue) while the MMA warp accumulates slice s + 1.
+// Items are ordered (pair, slice group, tile) with the tile fastest, so the CTAs that run at the same time read the same
+// target slices out of L2.  Same K order and the same epilogue code as conv_tc_kernel: bit-identical volume.
+constexpr int kCorrThreads = 384;       // warp 0: A producer, warp 2: B producer, warp 1: MMA issuer, warps 4..11: epilogue
+constexpr int kCorrBStages = 3;
+constexpr int kCorrABytes = 4 * kTileM * 128;              // 4 K chunks of 128 rows x 128 bytes
+constexpr int kCorrBBytes = 256 * 128;                     // one stage: 256 target rows x 64 channels
+constexpr int kCorrStageOff = kCorrABytes + kCorrBStages * kCorrBBytes;    // epilogue staging: 8 warps x 8 KiB
+constexpr int kCorrCtlOff = kCorrStageOff + 8 * 8192;
+
+struct CorrCtl {
+    uint64_t a_full, a_empty, b_full[kCorrBStages], b_empty[kCorrBStages], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kCorrThreads, 1)
+corr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const ConvGeom g, const ConvEpi e, const int group) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    CorrCtl* ctl = reinterpret_cast<CorrCtl*>(smem + kCorrCtlOff);
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+        mbar_init(&ctl->a_full, 1);
+        mbar_init(&ctl->a_empty, 1);
+        for (int s = 0; s < kCorrBStages; ++s) { mbar_init(&ctl->b_full[s], 1); mbar_init(&ctl->b_empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&ctl->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const int n_groups = (g.n_tiles + group - 1) / group;
+    const int per_pair = n_groups * g.tiles_x;
+    const int n_items = g.nbatch * per_pair;
+    bool ok = true;
+    // item i -> (pair b, slice group sg, source tile tx), tx fastest
+    auto decode = [&](int i, int& b, int& sg, int& tx) {
+        b = g.b0 + i / per_pair;
+        const int r = i - (i / per_pair) * per_pair;
+        sg = r / g.tiles_x;
+        tx = r - sg * g.tiles_x;
+    };
+    if (warp == 0) {
+        // ---- A producer: the item's source tile, all four K chunks on one barrier --------------------------------------------
+        uint32_t n = 0;
+        for (int i = blockIdx.x; i < n_items && ok; i += gridDim.x, ++n) {
+            int b, sg, tx;
+            decode(i, b, sg, tx);
+            if (!__all_sync(0xffffffffu, mbar_wait(&ctl->a_empty, (n & 1u) ^ 1u))) { ok = false; break; }
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&ctl->a_full, kCorrABytes);
+                for (int k = 0; k < 4; ++k) tma_load_4d(smem + k * (kTileM * 128), &tmA, &ctl->a_full, k * kChunkK, tx * g.tile_w, 0, b);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 2) {
+        // ---- B producer: target slices, 64-channel stages through the ring --------------------------------------------------
+        uint32_t st = 0, ph = 0;
+        for (int i = blockIdx.x; i < n_items && ok; i += gridDim.x) {
+            int b, sg, tx;
+            decode(i, b, sg, tx);
+            const int ny_end = min(g.n_tiles, (sg + 1) * group);
+            for (int ny = sg * group; ny < ny_end && ok; ++ny) {
+                const int brow = b * g.b_rows_per_batch + ny * g.n_tile;
+                for (int k = 0; k < 4; ++k) {
+                    if (!__all_sync(0xffffffffu, mbar_wait(&ctl->b_empty[st], ph ^ 1u))) { ok = false; break; }
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&ctl->b_full[st], kCorrBBytes);
+                        tma_load_2d(smem + kCorrABytes + st * kCorrBBytes, &tmB, &ctl->b_full[st], k * kChunkK, brow);
+                    }
+                    __syncwarp();
+                    if (++st == kCorrBStages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ----------------------------------------------------------------------------------------------------------
+        const uint32_t idesc = umma_idesc_f16(kTileM, 256);
+        const uint64_t d0 = umma_desc_k128(smem_u32(smem));
+        const uint32_t dhi = static_cast<uint32_t>(d0 >> 32), alo0 = static_cast<uint32_t>(d0);
+        const uint32_t blo0 = alo0 + (kCorrABytes >> 4);
+        uint32_t st = 0, ph = 0, n = 0, nacc = 0;
+        for (int i = blockIdx.x; i < n_items && ok; i += gridDim.x, ++n) {
+            int b, sg, tx;
+            decode(i, b, sg, tx);
+            if (!__all_sync(0xffffffffu, mbar_wait(&ctl->a_full, n & 1u))) { ok = false; break; }
+            const int ny_end = min(g.n_tiles, (sg + 1) * group);
+            for (int ny = sg * group; ny < ny_end && ok; ++ny, ++nacc) {
+                const uint32_t buf = nacc & 1u;
+                if (!__all_sync(0xffffffffu, mbar_wait(&ctl->acc_empty[buf], ((nacc >> 1) & 1u) ^ 1u))) { ok = false; break; }
+                tc_fence_after();
+                for (int k = 0; k < 4; ++k) {
+                    if (!__all_sync(0xffffffffu, mbar_wait(&ctl->b_full[st], ph))) { ok = false; break; }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t alo = alo0 + static_cast<uint32_t>(k) * ((kTileM * 128) >> 4);
+                        const uint32_t blo = blo0 + st * (kCorrBBytes >> 4);
+                        const uint32_t acc = tmem_base + buf * 256;
+                        umma_f16_lohi(acc, alo, dhi, blo, dhi, idesc, k != 0 ? 1u : 0u);
+                        umma_f16_lohi(acc, alo + 2, dhi, blo + 2, dhi, idesc, 1u);
+                        umma_f16_lohi(acc, alo + 4, dhi, blo + 4, dhi, idesc, 1u);
+                        umma_f16_lohi(acc, alo + 6, dhi, blo + 6, dhi, idesc, 1u);
+                        umma_commit(&ctl->b_empty[st]);
+                    }
+                    __syncwarp();
+                    if (++st == kCorrBStages) { st = 0; ph ^= 1u; }
+                }
+                if (ok && elect_one()) umma_commit(&ctl->acc_full[buf]);
+                __syncwarp();
+            }
+            if (ok && elect_one()) umma_commit(&ctl->a_empty);          // every MMA that reads this source tile has completed
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue warps: accumulator -> scale -> fp16 -> bulk tensor stores --------------------------------------------------
+        const int ew = warp - 4;
+        uint32_t nacc = 0;
+        for (int i = blockIdx.x; i < n_items && ok; i += gridDim.x) {
+            int b, sg, tx;
+            decode(i, b, sg, tx);
+            const int ny_end = min(g.n_tiles, (sg + 1) * group);
+            for (int ny = sg * group; ny < ny_end; ++ny, ++nacc) {
+                const uint32_t buf = nacc & 1u;
+                if (!mbar_wait(&ctl->acc_full[buf], (nacc >> 1) & 1u)) { ok = false; break; }
+                tc_fence_after();
+                tile_epilogue<EPI_F32>(g, e, smem + kCorrStageOff, nullptr, nullptr, tmem_base + buf * 256, ew, lane, tx, 0, b, ny, nullptr, &tmO);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->acc_empty[buf]);
+            }
+        }
+    }
+    if (!ok && e.err_flag != nullptr) atomicExch(e.err_flag, 40 + warp);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+const char* corr_gemm_launch(const ConvPlan& p, int nbatch, int b0, cudaStream_t stream) {
+    if (p.mode != EPI_F32 || p.variant != 1 || !p.e.tma_store || p.e.out16 == nullptr || p.g.n_tile != 256 || p.g.kchunks != 4 ||
+        p.g.ntaps != 1 || p.g.tile_h != 1 || p.g.b_rows_per_batch == 0)
+        return "corr_gemm_launch: not a bulk-store correlation plan (256 channels, 256-column slices)";
+    ConvGeom g = p.g;
+    g.nbatch = nbatch;
+    g.b0 = b0;
+    const int group = g.n_tiles <= 32 ? 4 : 8;
+    const int n_items = nbatch * ((g.n_tiles + group - 1) / group) * g.tiles_x;
+    static int n_sm = 0;
+    static bool attr_set = false;
+    const size_t smem = kCorrCtlOff + sizeof(CorrCtl) + 1024;
+    if (!attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t err = cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) return cudaGetErrorString(err);
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(n_items < n_sm ? n_items : n_sm));
+    cfg.blockDim = dim3(kCorrThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t lerr = cudaLaunchKernelEx(&cfg, corr_gemm_kernel, p.tmA, p.tmB, p.tmO, g, p.e, group);
+    if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? nullptr : cudaGetErrorString(err);
+}
+
 const char* conv_plan_enable_tma_store(ConvPlan* p, long rows) {
     p->e.tma_store = 0;
     if (p->mode != EPI_F32 || p->variant != 1) return "tma store: EPI_F32 plans of the 128-pixel kernel only";

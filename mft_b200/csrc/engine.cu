@@ -118,6 +118,7 @@ struct mftb200_ctx {
     CUtensorMap lk_tm[4];
     bool lk_tma_ok = false;
     int lookup_tma = 1;
+    int corr_persist = 1;                  // all-pairs correlation through corr_gemm_kernel (persistent) instead of conv_tc_kernel
     __half* E2[4] = {nullptr, nullptr, nullptr, nullptr};   // cnet's activation buffers (runs concurrently with fnet)
     // optional per-launch event profile (bench roofline): accumulated elapsed ms + launch count per kind
     int profile = 0;
@@ -362,7 +363,18 @@ const char* build_refine(mftb200_ctx* c, Builder& B) {
             c->corr_bulk_ok = conv_plan_enable_tma_store(&c->plans[i], static_cast<long>(mp) * npx) == nullptr;
             c->plans[i].e.tma_store = (c->corr_bulk_ok && c->corr_bulk) ? 1 : 0;
         }
-        c->pre_steps.push_back(B.step(i, true));
+        // the persistent correlation kernel (resident source tile, streamed target slices, double-buffered accumulators) when
+        // the volume leaves as bulk tensor stores; the per-(tile, slice) launch of conv_tc_kernel otherwise
+        mftb200_ctx::Step st = B.step(i, true);
+        auto plain = st.fn;
+        st.fn = [i, plain](mftb200_ctx* cc, cudaStream_t s) -> const char* {
+            if (i >= 0 && cc->corr_persist && !cc->conv_impl && cc->plans[i].e.tma_store && cc->plans[i].g.n_tile == 256) {
+                cc->launches++;
+                return corr_gemm_launch(cc->plans[i], cc->cur_pairs, cc->cur_b0, s);
+            }
+            return plain(cc, s);
+        };
+        c->pre_steps.push_back(st);
     }
     c->pre_steps.push_back([](mftb200_ctx* cc, cudaStream_t s) -> const char* {
         const size_t o = static_cast<size_t>(cc->cur_b0) * cc->npx;
@@ -1143,6 +1155,7 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
     }
     if (strcmp(key, "defer_context") == 0) { c->defer_context = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "lookup_tma") == 0) { c->lookup_tma = value ? 1 : 0; return MFTB200_OK; }
+    if (strcmp(key, "corr_persist") == 0) { c->corr_persist = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "conv_v2") == 0) { conv_set_v2(value & 1, (value >> 1) & 1); return MFTB200_OK; }   // bit0 on, bit1 base-offset
     if (strcmp(key, "pdl") == 0) { conv_set_pdl(value); return MFTB200_OK; }
     if (strcmp(key, "cluster") == 0) { conv_set_forced_cluster(value); return MFTB200_OK; }        // next configure()

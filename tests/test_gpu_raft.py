@@ -192,6 +192,33 @@ def test_corr_bulk_store_bit_identical(size, seeded_weights):
     assert torch.equal(res[0][0], res[1][0])
 
 
+@pytest.mark.parametrize('size', [(128, 160, 2), (136, 200, 3), (256, 256, 2), (512, 512, 3)])
+def test_persistent_correlation_bit_identical(size, seeded_weights):
+    """The all-pairs correlation through the persistent kernel (resident source tile, streamed target slices, two TMEM
+    accumulators) against the per-(tile, slice) launches of the plain conv kernel: same K order, same epilogue, so the
+    whole volume must agree bit for bit -- including ragged last tiles / slices (136x200: 425 coarse pixels)."""
+    from mft_b200.synth import synthetic_video
+    H, Wd, pairs = size
+    frames = list(synthetic_video(pairs + 1, H, Wd, seed=17))
+    eng = _engine(seeded_weights, H, Wd, pairs=pairs, slots=pairs + 1)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    n = ((H + 7) // 8) * ((Wd + 7) // 8)
+    lefts, rights = list(range(pairs)), [pairs] * pairs
+    res = {}
+    for mode in (1, 0, 1):
+        eng.set_option('corr_persist', mode)
+        out = eng.refine(lefts, rights).clone()
+        eng.check_device()
+        vol = eng.debug_buffer('corr_l0', torch.float16, (pairs, n, n)).clone()
+        if mode in res:
+            assert torch.equal(res[mode][1], vol)
+        res[mode] = (out, vol)
+    assert float(res[1][1].float().abs().max()) > 0
+    assert torch.equal(res[0][1], res[1][1]), (res[0][1].float() - res[1][1].float()).abs().max().item()
+    assert torch.equal(res[0][0], res[1][0])
+
+
 def test_pinned_frame_is_read_in_place(seeded_weights):
     """A frame in page-locked host memory is DMA'd straight from the caller's buffer; same features as the staged path."""
     from mft_b200 import _lib

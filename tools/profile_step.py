@@ -12,11 +12,11 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from mft_b200.synth import synthetic_video  # noqa: E402
 
-size = int(os.environ.get('PROFILE_SIZE', '512'))
+H, W = bench.parse_size(os.environ.get('PROFILE_SIZE', ''), 512)          # N or HxW
 steps = int(os.environ.get('PROFILE_STEPS', '1'))
 weights, _ = bench.load_weights()
 trk = bench.make_tracker(weights)
-frames = [torch.from_numpy(f).cuda() for f in synthetic_video(bench.STEADY + 4 + steps, size, size, seed=1234)]
+frames = [torch.from_numpy(f).cuda() for f in synthetic_video(bench.STEADY + 4 + steps, H, W, seed=1234)]
 trk.init(frames[0].cpu().numpy())
 for kv in filter(None, os.environ.get('BENCH_ENGINE_OPTIONS', '').split(',')):      # same A/B knobs as bench.py
     k, v = kv.split('=')
