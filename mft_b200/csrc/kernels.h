@@ -84,9 +84,11 @@ struct LookupArgs {
 cudaError_t launch_lookup(const LookupArgs& a, cudaStream_t stream);
 
 // The same lookup with the correlation windows fetched by the TMA unit: level l of the pyramid is a 3-D fp16 tensor
-// (x: w_l, y: h_l, row: pair * Npx + n); ONE 24 x 10 box per (pixel, level), starting at a multiple of 8 columns, lands in shared memory, out-of-map taps arrive
-// as zeros (= grid_sample's zero padding), no per-element address arithmetic or bounds handling in the SM.  Needs every
-// level's width to be a multiple of 8 (16-byte row pitch).  Bit-identical to launch_lookup.
+// (x: w_l, y: h_l, row: pair * Npx + n) with row pitch LookupArgs::pitch[l]; ONE 24 x 10 box per (pixel, level), starting at
+// a multiple of 8 columns (the innermost TMA coordinate must be 16-byte aligned), lands in shared memory; out-of-map taps
+// arrive as zeros (= grid_sample's zero padding): no per-element address arithmetic or bounds handling in the SM.  Needs
+// every level's row pitch to be a multiple of 8 elements, i.e. a coarse width that is a multiple of 8 (the engine pads the
+// pooled levels' rows).  Bit-identical to launch_lookup.
 struct LookupTmaArgs {
     CUtensorMap tm[4];
     LookupArgs a;                    // a.lvl is not read; the other pointers start at row pix0
