@@ -27,6 +27,8 @@ Other workloads of BASELINE.json (not run by the driver's default command line):
   --mode tapvid       config 3: synthetic TAP-Vid-schema dataset (256x256 -> 512x512), first + strided query modes,
                       forward + backward tracking with the device flow cache, sequences round-robin over ranks
   --size HxW          config 5: e.g. --size 1080x1920 (one sequence per GPU, full delta set)
+  --mode demo         config 2: the reference's demo video, full length, 512x512, full delta set, one GPU: init + track of
+                      every frame as demo.py does (numpy frames in, CPU result out), wall clock and device time
 """
 import argparse
 import json
@@ -768,13 +770,68 @@ def run_tapvid(args):
         dist.destroy_process_group()
 
 
+def run_demo(args):
+    """BASELINE config 2: demo.py's loop over the whole demo video at 512x512 (init on frame 0, track every other frame,
+    pageable numpy frames in, CPU results out, point queries converted per frame like demo.py:59-69)."""
+    import torch
+    from mft_b200.point_tracking import convert_to_point_tracking
+    from mft_b200.synth import demo_video_frames
+    H, W = parse_size(args.size, 512)
+    frames = demo_video_frames((W, H))
+    if len(frames) < 3:
+        print(json.dumps({'metric': 'dense-track frames/sec', 'unavailable': 'demo video not reachable on this box'}), flush=True)
+        return
+    torch.cuda.set_device(0)
+    weights, wsrc = load_weights()
+    tracker = make_tracker(weights)
+    yy, xx = np.mgrid[20:H - 10:30, 20:W - 10:30]
+    queries = torch.from_numpy(np.stack([xx.ravel(), yy.ravel()], 1).astype(np.float32)).cuda()
+
+    def run(device_frames):
+        src = [torch.from_numpy(f).cuda() for f in frames] if device_frames else frames
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        tracker.init(src[0])
+        for f in src[1:]:
+            meta = tracker.track(f, device_result=device_frames)
+            if not device_frames:
+                convert_to_point_tracking(meta.result, queries)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3, time.perf_counter() - t0, meta
+
+    run(True)                                                    # warm-up pass (allocations, clocks)
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.resume()
+    dev_s, _, _ = run(True)
+    _, e2e_s, meta = run(False)
+    clocks = sampler.stop()
+    tracker.engine.check_device()
+    n = len(frames)
+    assert tuple(meta.result.flow.shape) == (2, H, W) and not meta.result.flow.is_cuda
+    line = {
+        'metric': 'dense-track frames/sec', 'value': n / dev_s, 'unit': 'frames/s', 'n_gpus': 1, 'steps': n, 'warmup': n,
+        'ms_per_step': dev_s / n * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'demo video',
+        'config': {'workload': f'demo_in video, all {n} frames resized to {W}x{H}, deltas [inf,1,2,4,8,16,32], 12 GRU iters: init + track of every frame '
+                               '(the first 32 frames run fewer than 7 chains), as demo.py', 'weights': wsrc,
+                   'cache': 'per-frame working set (7 correlation pyramids, 300 MB) exceeds the L2; no flush',
+                   'e2e': 'pageable numpy frames in, CPU FlowOUTrackingResult out, 272 point queries converted per frame (demo.py:59-69)'},
+        'e2e': {'value': n / e2e_s, 'unit': 'frames/s', 'h2d_bytes_per_step': H * W * 3, 'd2h_bytes_per_step': 16 * H * W},
+        'gpu_launches': int(tracker.engine.launch_count()), 'clocks': clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='track', choices=['track', 'flow-shard', 'tapvid'])
+    ap.add_argument('--mode', default='track', choices=['track', 'flow-shard', 'tapvid', 'demo'])
     ap.add_argument('--size', default='', help='frame size: N or HxW (default 512; 1024 for --mode flow-shard)')
     ap.add_argument('--iters', type=int, default=0, help='GRU iterations for --mode flow-shard (default 32)')
     ap.add_argument('--sequences', type=int, default=8, help='--mode tapvid: number of synthetic sequences')
@@ -791,6 +848,8 @@ def main():
         run_flow_shard(args)
     elif args.mode == 'tapvid':
         run_tapvid(args)
+    elif args.mode == 'demo':
+        run_demo(args)
     else:
         run_ours(args)
 

@@ -47,3 +47,34 @@ def synthetic_video(T, H, W, seed=1234, max_motion=2.5, n_rects=3):
             y0 = int(round((r['p'][1] + r['v'][1] * t) % (H - rh)))
             frame[y0:y0 + rh, x0:x0 + rw] = r['tex']
         yield np.ascontiguousarray(frame)
+
+
+DEMO_VIDEO_REL = 'demo_in/ugsJtsO9w1A-00.00.24.457-00.00.29.462_HD.mp4'       # the reference's demo input (demo.py)
+
+
+def find_demo_video():
+    """Path of the reference's demo video if it is reachable (it is DATA: $MFT_DEMO_VIDEO, the copy that travels with the
+    repo snapshot, a reference checkout); None otherwise."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.environ.get('MFT_DEMO_VIDEO', ''), os.path.join(root, 'oracle', '_ref', 'demo_video.mp4'),
+              os.path.join(os.environ.get('MFT_REFERENCE_ROOT', '/root/reference'), DEMO_VIDEO_REL)):
+        if p and os.path.isfile(p):
+            return p
+    return None
+
+
+def demo_video_frames(size=(512, 512), max_frames=None):
+    """All frames of the demo video as uint8 BGR, resized with cv2.INTER_AREA to (W, H) = size (BASELINE config 2)."""
+    path = find_demo_video()
+    if path is None:
+        return []
+    cap = cv2.VideoCapture(path)
+    frames = []
+    while max_frames is None or len(frames) < max_frames:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(np.ascontiguousarray(cv2.resize(f, size, interpolation=cv2.INTER_AREA)))
+    cap.release()
+    return frames
