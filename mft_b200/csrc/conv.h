@@ -145,6 +145,8 @@ struct ConvProgram {
     ProgLayer L[kMaxProgLayers];
     int n_layers;
     int tickets;                  // tiles a CTA may hold at once (scheduler run-ahead), 1..4; 0 = 4
+    int static_order;             // 1: CTA c runs the items c, c + G, c + 2G, ... of the (iteration, layer, pair, tile) order and polls
+                                  // each item's arrival counter itself -- no ready queue (no tail atomic, no queue round trip)
     int iters;                    // the whole layer sequence is repeated `iters` times (iterations overlap tile by tile)
     LookupArgs lk;                // operands of the lookup layer, if any
     int nbatch, b0;               // batch entries covered by this launch

@@ -660,6 +660,7 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
         }
         const unsigned long long tag = static_cast<unsigned long long>(P.epoch) << 32;
         auto push = [&](uint32_t item) {
+            if (P.static_order) return;             // the item's own CTA polls its arrival counter
             const unsigned long long slot = atomicAdd(P.tail, 1ull) - P.tail_base;
             st_release_gpu_u64(P.queue + slot, tag | item);
         };
@@ -725,7 +726,8 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                 if (__shfl_sync(0xffffffffu, room, 0) != 0u) {
                     if (!have_idx) {
                         if (lane == 0) {
-                            const unsigned long long d = atomicAdd(P.head, 1ull) - P.head_base;
+                            const unsigned long long d = P.static_order ? static_cast<unsigned long long>(blockIdx.x) + static_cast<unsigned long long>(n_issue) * gridDim.x
+                                                                        : atomicAdd(P.head, 1ull) - P.head_base;
                             idx = d < total ? static_cast<uint32_t>(d) : kTicketEnd;
                         }
                         idx = __shfl_sync(0xffffffffu, idx, 0);
@@ -741,7 +743,24 @@ conv_prog_kernel(const __grid_constant__ ConvProgram P) {
                         progress = true;
                     } else {
                         unsigned long long entry = 0;
-                        if (lane == 0) entry = ld_acquire_gpu_u64(P.queue + idx);
+                        if (P.static_order) {
+                            // item idx itself: ready when every round of arrivals up to its iteration is in (roots: at once)
+                            if (lane == 0) {
+                                int its, sl, b, nt;
+                                prog_decode(P, idx, its, sl, b, nt);
+                                const ProgLayer& S = P.L[sl];
+                                const int rounds = its - S.iter_shift + 1;
+                                bool ready = S.n_dep == 0 || rounds <= 0;
+                                if (!ready) {
+                                    const int nty = nt / P.tiles_x, ntx = nt - nty * P.tiles_x;
+                                    const int nn = (1 + min(S.rx, ntx) + min(S.rx, P.tiles_x - 1 - ntx)) * (1 + min(S.ry, nty) + min(S.ry, P.tiles_y - 1 - nty));
+                                    ready = ld_acquire_gpu(arr_cur + (static_cast<long>(sl * P.max_batch + b) * tpp + nt)) >= rounds * S.n_dep * nn;
+                                }
+                                entry = ready ? ((static_cast<unsigned long long>(P.epoch) << 32) | idx) : 0ull;
+                            }
+                        } else if (lane == 0) {
+                            entry = ld_acquire_gpu_u64(P.queue + idx);
+                        }
                         entry = __shfl_sync(0xffffffffu, entry, 0);
                         if ((entry >> 32) == P.epoch) {
                             const uint32_t item = static_cast<uint32_t>(entry);
@@ -1828,8 +1847,10 @@ const char* conv_prog_launch(ConvProgram* prog, int nbatch, int b0, int iters, c
     cudaError_t lerr = has_lookup ? cudaLaunchKernelEx(&cfg, conv_prog_kernel<true>, *prog)
                                   : cudaLaunchKernelEx(&cfg, conv_prog_kernel<false>, *prog);
     // every CTA pops until it sees a ticket >= total: head advances by total + grid per launch, tail by total
-    prog->head_base += static_cast<unsigned long long>(total + grid);
-    prog->tail_base += static_cast<unsigned long long>(total);
+    if (!prog->static_order) {                     // (the static order touches neither counter)
+        prog->head_base += static_cast<unsigned long long>(total + grid);
+        prog->tail_base += static_cast<unsigned long long>(total);
+    }
     if (lerr != cudaSuccess) return cudaGetErrorString(lerr);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? nullptr : cudaGetErrorString(err);

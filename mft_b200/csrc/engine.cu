@@ -1147,6 +1147,10 @@ int mftb200_set_option(mftb200_ctx* c, const char* key, int value) {
         return MFTB200_OK;
     }
     if (strcmp(key, "prog_tickets") == 0) { c->prog.tickets = c->prog_full.tickets = value; return MFTB200_OK; }
+    if (strcmp(key, "prog_static") == 0) {            // static round-robin tile order instead of the ready queue (A/B knob)
+        c->prog.static_order = c->prog_full.static_order = c->prog_heads.static_order = value ? 1 : 0;
+        return MFTB200_OK;
+    }
     if (strcmp(key, "profile") == 0) { c->profile = value ? 1 : 0; return MFTB200_OK; }
     if (strcmp(key, "corr_bulk_store") == 0) {
         c->corr_bulk = value ? 1 : 0;

@@ -354,6 +354,32 @@ def test_tma_lookup_bit_identical(geom, seeded_weights):
     assert torch.equal(res[1][0], res[0][0])
 
 
+@pytest.mark.parametrize('geom', [(128, 160, 5), (256, 256, 7), (512, 512, 7)])
+def test_program_static_order_bit_identical(geom, seeded_weights):
+    """Engine option prog_static: every CTA of the program kernel runs a fixed round-robin share of the (iteration, layer,
+    pair, tile) order and polls the arrival counters itself instead of popping a ready queue.  Same tiles, same arithmetic:
+    not a bit may differ, for the per-iteration program, the heads program and the all-iterations program."""
+    from mft_b200.synth import synthetic_video
+    H, Wd, pairs = geom
+    frames = list(synthetic_video(pairs + 1, H, Wd, seed=29))
+    eng = _engine(seeded_weights, H, Wd, pairs=pairs, slots=pairs + 1)
+    for i, f in enumerate(frames):
+        eng.encode_frame(f, i)
+    lefts, rights = list(range(pairs)), [pairs] * pairs
+    ref = eng.refine(lefts, rights).clone()
+    for mode in (1, 2):
+        eng.set_option('persist', mode)
+        for static in (1, 0, 1):
+            eng.set_option('prog_static', static)
+            got = eng.refine(lefts, rights).clone()
+            eng.check_device()
+            assert torch.equal(ref, got), (geom, mode, static, (ref - got).abs().max().item())
+            got1 = eng.refine(lefts[:2], rights[:2]).clone()
+            eng.check_device()
+            assert torch.equal(ref[:2], got1), (geom, mode, static)
+    eng.set_option('prog_static', 0)
+
+
 def test_program_column_split_bit_identical(seeded_weights):
     """Global option prog_split_n: the 256-column layers of the iteration program (convc1, z|r, flow head 1) as two
     128-column work items per tile.  An output column's K order does not depend on the column tiling, so not a single bit
