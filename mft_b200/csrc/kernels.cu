@@ -717,7 +717,6 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
         __syncwarp();                                                      // every box of this level is in registers: the window may overwrite them
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
-            const int T = lane + 32 * r;
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v[r].x));
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v[r].y));
             *reinterpret_cast<float4*>(w + dst_off[r]) = make_float4(f0.x, f0.y, f1.x, f1.y);
