@@ -1643,7 +1643,7 @@ corr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int ny_end = min(g.n_tiles, (sg + 1) * group);
             for (int ny = sg * group; ny < ny_end; ++ny, ++nacc) {
                 const uint32_t buf = nacc & 1u;
-                if (!mbar_wait(&ctl->acc_full[buf], (nacc >> 1) & 1u)) { ok = false; break; }
+                if (!__all_sync(0xffffffffu, mbar_wait(&ctl->acc_full[buf], (nacc >> 1) & 1u))) { ok = false; break; }
                 tc_fence_after();
                 tile_epilogue<EPI_F32>(g, e, smem + kCorrStageOff, nullptr, nullptr, tmem_base + buf * 256, ew, lane, tx, 0, b, ny, nullptr, &tmO);
                 tc_fence_before();

@@ -701,7 +701,7 @@ lookup_tma_kernel(const __grid_constant__ LookupTmaArgs P, const long n_groups) 
     }
 #pragma unroll
     for (int l = 3; l >= 0; --l) {
-        if (!mbar_wait(&bar[wib][l & 1], l < 2 ? 1u : 0u)) {               // (each barrier completes twice: levels 3 | 2, then 1 | 0)
+        if (!__all_sync(0xffffffffu, mbar_wait(&bar[wib][l & 1], l < 2 ? 1u : 0u))) {      // (each barrier completes twice: levels 3 | 2, then 1 | 0; warp-uniform verdict)
             if (lane == 0 && P.err_flag != nullptr) atomicExch(P.err_flag, 90);
             return;
         }

@@ -446,3 +446,23 @@ def test_tapvid_runner_host_logic():
             assert abs(tracks[k, t, 0] - (x + (t - s))) < 1e-4 and abs(tracks[k, t, 1] - y) < 1e-4
     tracks_f, _, n_f = TV.run_sequence(FakeTracker(), video, qf, 'first', device='cpu')
     assert n_f == sum(12 - s for s in sorted(set(qf[:, 0].astype(int))))
+
+
+def test_demo_video_helper():
+    """bench.py --mode demo (BASELINE config 2) reads the reference's demo video as DATA through mft_b200.synth."""
+    from mft_b200.synth import demo_video_frames, find_demo_video
+    if find_demo_video() is None:
+        pytest.skip('demo video not reachable here')
+    fr = demo_video_frames((96, 64), max_frames=3)
+    assert len(fr) == 3 and fr[0].shape == (64, 96, 3) and fr[0].dtype == np.uint8 and fr[0].flags.c_contiguous
+    assert any(not np.array_equal(fr[0], f) for f in fr[1:])
+
+
+def test_bench_modes_parse():
+    """The bench's command line keeps the driver's contract (defaults: one GPU, 20 steps, 3 warm-up) and names every mode."""
+    import bench
+    assert bench.parse_size('', 512) == (512, 512) and bench.parse_size('1080x1920', 512) == (1080, 1920) and bench.parse_size('1024', 512) == (1024, 1024)
+    src = open(bench.__file__).read()
+    for mode in ('track', 'flow-shard', 'tapvid', 'demo'):
+        assert f"'{mode}'" in src
+    assert abs(bench.flops_per_frame(512, 512) - 2092426067968) < 1
