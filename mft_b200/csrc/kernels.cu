@@ -475,15 +475,21 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
     float* s2 = sm + h1 * w1;
     const long row = blockIdx.x;
     const __half* src = L0 + row * h * w;
+    // (per-row base pointers once, 32-bit unsigned index arithmetic inside the loops: the kernel is instruction-issue bound)
+    __half* const o1 = L1 + row * h1 * p1;
+    __half* const o2 = L2 + row * h2 * p2;
+    __half* const o3 = L3 + row * h3 * p3;
+    const unsigned uw = static_cast<unsigned>(w), uw1 = static_cast<unsigned>(w1), uw2 = static_cast<unsigned>(w2), uw3 = static_cast<unsigned>(w3);
     // every level is the fp32 average of the level above as it is STORED (fp16), rounded once: what avg_pool2d of the
     // stored volume gives (core/corr.py:26-28)
     if ((w & 7) == 0) {
         // 16-byte loads: one thread = 8 columns of the row pair (2y, 2y+1) -> 4 outputs, one 8-byte store
-        const int w8 = w >> 3;
-        for (int i = threadIdx.x; i < h1 * w8; i += blockDim.x) {
-            const int y = i / w8, g = i - y * w8;
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + (2 * y) * w) + g);
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + (2 * y + 1) * w) + g);
+        const unsigned w8 = uw >> 3, n1 = static_cast<unsigned>(h1) * w8;
+        for (unsigned i = threadIdx.x; i < n1; i += blockDim.x) {
+            const unsigned y = i / w8, g = i - y * w8;
+            const uint4* p = reinterpret_cast<const uint4*>(src + 2u * y * uw) + g;
+            const uint4 a = __ldg(p);
+            const uint4 b = __ldg(p + w8);
             const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
             __half r[4];
             float rf[4];
@@ -495,41 +501,48 @@ corr_pool_kernel(const __half* __restrict__ L0, __half* __restrict__ L1, __half*
                 rf[j] = __half2float(r[j]);
             }
             // (one 16-byte store: four scalar stores at a 4-word stride were 4-way bank conflicts; w1 is a multiple of 4 here)
-            *reinterpret_cast<float4*>(s1 + y * w1 + 4 * g) = make_float4(rf[0], rf[1], rf[2], rf[3]);
+            *reinterpret_cast<float4*>(s1 + y * uw1 + 4u * g) = make_float4(rf[0], rf[1], rf[2], rf[3]);
             const __half2 p01 = __halves2half2(r[0], r[1]), p23 = __halves2half2(r[2], r[3]);
-            *reinterpret_cast<uint2*>(L1 + (row * h1 + y) * p1 + 4 * g) =
+            *reinterpret_cast<uint2*>(o1 + y * static_cast<unsigned>(p1) + 4u * g) =
                 make_uint2(*reinterpret_cast<const uint32_t*>(&p01), *reinterpret_cast<const uint32_t*>(&p23));
         }
     } else {
-        for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
-            const int y = i / w1, x = i % w1;
-            const __half* q = src + (2 * y) * w + 2 * x;
+        const unsigned n1 = static_cast<unsigned>(h1) * uw1;
+        for (unsigned i = threadIdx.x; i < n1; i += blockDim.x) {
+            const unsigned y = i / uw1, x = i - y * uw1;
+            const __half* q = src + 2u * y * uw + 2u * x;
             const __half r = __float2half_rn((((__half2float(q[0]) + __half2float(q[1])) + __half2float(q[w])) + __half2float(q[w + 1])) * 0.25f);
             s1[i] = __half2float(r);
-            L1[(row * h1 + y) * p1 + x] = r;
+            o1[y * static_cast<unsigned>(p1) + x] = r;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
-        const int y = i / w2, x = i % w2;
-        const float* q = s1 + (2 * y) * w1 + 2 * x;
-        float2 t, u;
-        if ((w1 & 1) == 0) {                                               // even row pitch: the pairs are 8-byte aligned
-            t = *reinterpret_cast<const float2*>(q);
-            u = *reinterpret_cast<const float2*>(q + w1);
-        } else {
-            t = make_float2(q[0], q[1]);
-            u = make_float2(q[w1], q[w1 + 1]);
+    {
+        const unsigned n2 = static_cast<unsigned>(h2) * uw2;
+        for (unsigned i = threadIdx.x; i < n2; i += blockDim.x) {
+            const unsigned y = i / uw2, x = i - y * uw2;
+            const float* q = s1 + 2u * y * uw1 + 2u * x;
+            float2 t, u;
+            if ((w1 & 1) == 0) {                                           // even row pitch: the pairs are 8-byte aligned
+                t = *reinterpret_cast<const float2*>(q);
+                u = *reinterpret_cast<const float2*>(q + w1);
+            } else {
+                t = make_float2(q[0], q[1]);
+                u = make_float2(q[w1], q[w1 + 1]);
+            }
+            const __half r = __float2half_rn((((t.x + t.y) + u.x) + u.y) * 0.25f);
+            s2[i] = __half2float(r);
+            o2[y * static_cast<unsigned>(p2) + x] = r;
         }
-        const __half r = __float2half_rn((((t.x + t.y) + u.x) + u.y) * 0.25f);
-        s2[i] = __half2float(r);
-        L2[(row * h2 + y) * p2 + x] = r;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < h3 * w3; i += blockDim.x) {
-        const int y = i / w3, x = i % w3;
-        const float* q = s2 + (2 * y) * w2 + 2 * x;
-        L3[(row * h3 + y) * p3 + x] = __float2half_rn((((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f);
+    {
+        const unsigned n3 = static_cast<unsigned>(h3) * uw3;
+        for (unsigned i = threadIdx.x; i < n3; i += blockDim.x) {
+            const unsigned y = i / uw3, x = i - y * uw3;
+            const float* q = s2 + 2u * y * uw2 + 2u * x;
+            o3[y * static_cast<unsigned>(p3) + x] = __float2half_rn((((q[0] + q[1]) + q[w2]) + q[w2 + 1]) * 0.25f);
+        }
     }
 }
 
