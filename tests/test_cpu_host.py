@@ -256,17 +256,39 @@ def _run_delta_sharded(world):
 
 
 def _run_sharded(world):
+    """Per-timestep flow sharding as bench.py --mode flow-shard drives it: the encoders are sharded too (rank t % G "encodes"
+    frame t, one feature all_gather per round through encode_fn), the flows depend on the GATHERED features of both frames,
+    and the scan continues across two run_range calls (state-building part, then the timed part)."""
+    import torch.distributed as dist
     from mft_b200.dist import FlowShardedTracker
-    H, W, T = 6, 8, 11
+    H, W, T = 6, 8, 13
     deltas = [np.inf, 1, 2, 4]
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    feats = torch.zeros(T + world, 3)
+    feats[0] = 0.5                                             # the template: every rank encodes it itself
+    encoded = []
 
-    def flow_fn(t, live, out=None):        # deterministic stand-in for encode + refine
-        return torch.stack([torch.full((4, H, W), float(t * 10 + (0 if np.isinf(d) else d))) for d, _ in live])
+    def encode_fn(ts):
+        t0 = ts[0]
+        mine = t0 + rank
+        if mine < T:
+            feats[mine] = 1.5 * mine + 0.25                    # only the owner computes the frame's features
+            encoded.append(mine)
+        if world > 1:
+            blk = feats[t0:t0 + world]
+            dist.all_gather_into_tensor(blk.view(world * 3), feats[t0 + rank].clone())
+
+    def flow_fn(t, live, out=None):        # deterministic stand-in for the batched refinement: reads both frames' features
+        return torch.stack([torch.full((4, H, W), float(t * 10 + (0 if np.isinf(d) else d)) + float(feats[left].sum() * 0.125 + feats[t].sum()))
+                            for d, left in live])
 
     def select_fn(lefts, right):  # deterministic stand-in for chain_select
         return sum(l * 0.5 for l in lefts) / len(lefts) + right.mean(0)
-    trk = FlowShardedTracker(deltas, T, (H, W), flow_fn, select_fn, 'cpu')
-    res = trk.run()
+    trk = FlowShardedTracker(deltas, T, (H, W), flow_fn, select_fn, 'cpu', encode_fn=encode_fn)
+    split = 1 + 3 * world                                      # a round boundary
+    trk.run_range(1, split)
+    res = trk.run_range(split, T)
+    assert encoded == [t for t in range(1, T) if (t - 1) % world == rank]      # every frame encoded once, by its owner
     return {k: float(v.sum()) for k, v in res.items()}
 
 
