@@ -269,6 +269,27 @@ def test_parked_context_is_ordered_before_its_readers(seeded_weights):
     assert torch.equal(first, again)
 
 
+def test_context_schedules_bit_identical(seeded_weights):
+    """Engine option defer_context: 1 (default) parks the context encoder behind the frame's refinement on the engine's own
+    stream; 0 runs it beside fnet on the side stream (which fnet's down-sampling branches also use).  Same kernels, same
+    inputs: the feature slots and the refinement must not differ by a bit."""
+    from mft_b200.synth import synthetic_video
+    frames = list(synthetic_video(4, 256, 320, seed=15))
+    res = {}
+    for mode in (1, 0):
+        eng = _engine(seeded_weights, 256, 320, pairs=2, slots=4)
+        eng.set_option('defer_context', mode)
+        for i, f in enumerate(frames):
+            eng.encode_frame(f, i)
+        out = eng.refine([0, 1], [3, 2]).clone()
+        out2 = eng.refine([3], [1]).clone()                   # the newest frame as LEFT image
+        eng.check_device()
+        res[mode] = (out, out2, [x.clone() for x in eng.slot_tensors()])
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for a, b in zip(res[0][2], res[1][2]):
+        assert torch.equal(a, b)
+
+
 def test_batched_equals_single_pair(seeded_weights):
     """A pair's result must not depend on what else is in the batch (bit-exact)."""
     from mft_b200.synth import synthetic_video
